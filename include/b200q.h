@@ -1,0 +1,224 @@
+/*
+ * b200q.h — C ABI of libb200q.so, the B200-native (sm_100a) generation engine that
+ * replaces the arithmetic behind llmq's vLLM worker.
+ *
+ * The reference (iPieter/llmq) has NO FFI of its own: its hot path is four Python calls
+ * into the un-vendored vLLM package (ref:llmq/workers/vllm_worker.py:105-123 engine
+ * construction, :146 tokenizer, :161-165 sampling params, :183-186 engine.generate).
+ * Each group of entry points below cites the reference call (or the vLLM op behind it)
+ * that it replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types in any signature.
+ *   - every function returns 0 on success or a negative B200Q_E* code; it never throws.
+ *     b200q_last_error() returns a thread-local message for the last failure.
+ *   - all `dev` pointers are device pointers owned by the caller (PyTorch is only the
+ *     allocator); the library owns TMA descriptors, small metadata buffers and its
+ *     scheduler state.
+ *   - no hidden synchronisation in the op-level and model-level calls: work is enqueued
+ *     on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *     Engine-level calls (b200q_engine_step) synchronise their own stream because they
+ *     hand token ids back to the host.
+ *   - bf16 tensors are passed as `void*` / `const void*` (2-byte elements, row-major).
+ */
+#ifndef B200Q_H_
+#define B200Q_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200Q_VERSION 1
+
+#define B200Q_OK 0
+#define B200Q_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define B200Q_ECUDA (-2)    /* CUDA runtime / driver error                 */
+#define B200Q_ENOMEM (-3)   /* KV pool or workspace exhausted              */
+#define B200Q_ESTATE (-4)   /* call made in the wrong state (unbound etc.) */
+#define B200Q_ENODEV (-5)   /* no sm_100 device present                    */
+
+int b200q_version(void);
+const char* b200q_last_error(void);
+/* 0 if a CUDA device with compute capability 10.x is current, else B200Q_ENODEV. */
+int b200q_device_check(void);
+
+/* ------------------------------------------------------------------------------------
+ * Op-level entry points (used by the parity tests and by b200q_model_forward).
+ * Each replaces one op vLLM dispatches for the reference worker.
+ * ---------------------------------------------------------------------------------- */
+
+/* K1  embedding gather: out[t,:] = table[ids[t],:]            (vLLM VocabParallelEmbedding) */
+int b200q_embed(const int32_t* ids_dev, const void* table_dev, void* out_dev,
+                int T, int H, void* stream);
+
+/* K2  RMSNorm: y = bf16(bf16(x * rsqrt(mean(x^2)+eps)) * w)      (vllm/ir/ops/layernorm.py:9-21) */
+int b200q_rmsnorm(const void* x_dev, const void* w_dev, void* y_dev,
+                  int T, int H, float eps, void* stream);
+
+/* K2' fused residual add + RMSNorm, in place:
+ *     residual <- bf16(x + residual);  x <- rmsnorm(residual) * w
+ *     (vllm/ir/ops/layernorm.py:39-58; rounding of the sum as in vLLM's _C kernel / HF) */
+int b200q_add_rmsnorm(void* x_dev, void* residual_dev, const void* w_dev,
+                      int T, int H, float eps, void* stream);
+
+/* K4+K5  neox RoPE on q,k (in place on the fused qkv rows) and scatter of k,v into the
+ *     paged KV cache.  qkv: [T, (n_q + 2*n_kv) * D]; cos_sin: bf16 [max_pos, D] (cos | sin);
+ *     slot_mapping[t] = block * block_size + offset, or < 0 to skip the cache write.
+ *     (vllm rotary_embedding/base.py:140-180 + _C_cache_ops.reshape_and_cache_flash) */
+int b200q_rope_kvwrite(void* qkv_dev, const void* cos_sin_dev, const int32_t* positions_dev,
+                       const int32_t* slot_mapping_dev, void* kv_layer_dev,
+                       int T, int n_q, int n_kv, int D, int block_size, void* stream);
+
+/* K7  paged decode attention (one query token per sequence, GQA).
+ *     q rows are the first n_seqs rows of the fused qkv buffer (row stride q_stride elems);
+ *     out: [n_seqs, n_q * D].  kv_layer: [num_blocks][2][n_kv][block_size][D] bf16, each
+ *     token row stored with its 16-byte chunks XOR-swizzled by (token_in_block & 7).
+ *     (replaces flashinfer trtllm_batch_decode_with_kv_cache, vllm flashinfer.py:1803) */
+int b200q_decode_attn(const void* q_dev, int q_stride, void* out_dev, const void* kv_layer_dev,
+                      const int32_t* block_table_dev, int bt_stride, const int32_t* ctx_lens_dev,
+                      int n_seqs, int n_q, int n_kv, int D, int block_size, float scale,
+                      void* stream);
+
+/* K6  paged causal prefill attention over q-tiles of <=16 consecutive tokens of one sequence.
+ *     tiles: int32[n_tiles][4] = {block_table_row, first_batch_row, n_rows, first_position}.
+ *     (replaces flashinfer trtllm_batch_context_with_kv_cache, vllm flashinfer.py:1665) */
+int b200q_prefill_attn(const void* q_dev, int q_stride, void* out_dev, const void* kv_layer_dev,
+                       const int32_t* block_table_dev, int bt_stride, const int32_t* tiles_dev,
+                       int n_tiles, int n_q, int n_kv, int D, int block_size, float scale,
+                       void* stream);
+
+/* K3/K8/K9/K11/K12  C[M,N] = A[M,K] * W[N,K]^T, bf16 in, fp32 accumulate in TMEM (tcgen05),
+ *     bf16 out.  A, W, C row-major and contiguous; K % 64 == 0, N % 64 == 0.
+ *     (replaces F.linear -> cuBLASLt, vllm/model_executor/layers/utils.py:92-98) */
+int b200q_gemm_bf16(const void* A_dev, const void* W_dev, void* C_dev,
+                    int M, int N, int K, void* stream);
+
+/* K10 SwiGLU: out[t,i] = bf16(bf16(silu(g[t,i])) * u[t,i]), gate_up = [T, 2I] = (g | u)
+ *     (vllm activation.py:138-141 SiluAndMul.forward_native) */
+int b200q_swiglu(const void* gate_up_dev, void* out_dev, int T, int I, void* stream);
+
+/* row gather: out[i,:] = x[rows[i],:]  (last-token selection before the LM head) */
+int b200q_gather_rows(const void* x_dev, const int32_t* rows_dev, void* out_dev,
+                      int n, int H, void* stream);
+
+/* K13 greedy sampler: ids[b] = argmax_v logits[b,v] over bf16 logits, lowest index wins ties
+ *     (vllm/v1/sample/sampler.py:91,235-236 in the oracle's temperature-0 mode) */
+int b200q_argmax_bf16(const void* logits_dev, int32_t* ids_dev, int B, int V, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Model-level: one forward step over a mixed decode+prefill token batch.
+ * Replaces GPUModelRunner.execute_model for LlamaForCausalLM
+ * (vllm/model_executor/models/llama.py:316-333,395-431).
+ * ---------------------------------------------------------------------------------- */
+
+typedef struct b200q_model_config {
+  int32_t hidden;        /* H                              */
+  int32_t n_layers;      /* L                              */
+  int32_t n_q_heads;
+  int32_t n_kv_heads;
+  int32_t head_dim;      /* 64 or 128                      */
+  int32_t intermediate;  /* I                              */
+  int32_t vocab;         /* V                              */
+  int32_t block_size;    /* KV page size in tokens (16)    */
+  int32_t max_tokens;    /* workspace capacity: max tokens per step */
+  int32_t max_seqs;      /* max sequences per step (block-table rows, sampled rows) */
+  int32_t max_pos;       /* rows of the RoPE table         */
+  int32_t tie_embeddings;/* 1: lm_head shares embed_tokens */
+  float rms_eps;
+  float attn_scale;      /* 1/sqrt(head_dim)               */
+} b200q_model_config;
+
+typedef struct b200q_model* b200q_model_t;
+
+/* device metadata for one step; every pointer is a device pointer to int32 data */
+typedef struct b200q_batch {
+  int32_t T;             /* total tokens this step; decode tokens occupy rows [0, n_dec)        */
+  int32_t n_dec;         /* decode sequences (1 token each); block-table rows [0, n_dec)        */
+  int32_t n_tiles;       /* prefill q-tiles                                                     */
+  int32_t n_sample;      /* rows for which a next token is sampled                              */
+  int32_t bt_stride;     /* int32 elements per block-table row                                  */
+  const int32_t* token_ids;     /* [T]                                                          */
+  const int32_t* positions;     /* [T]                                                          */
+  const int32_t* slot_mapping;  /* [T]                                                          */
+  const int32_t* block_table;   /* [rows][bt_stride]                                            */
+  const int32_t* ctx_lens;      /* [n_dec] context length including the current token           */
+  const int32_t* tiles;         /* [n_tiles][4]                                                 */
+  const int32_t* sample_rows;   /* [n_sample] batch rows whose hidden state feeds the LM head   */
+  int32_t* out_ids;             /* [n_sample] sampled token ids                                 */
+} b200q_batch;
+
+int b200q_model_create(const b200q_model_config* cfg, b200q_model_t* out);
+int b200q_model_destroy(b200q_model_t m);
+/* names: "embed", "final_norm", "lm_head", and per layer i: "layers.i.input_norm",
+ * "layers.i.qkv" [(n_q+2n_kv)D, H], "layers.i.o" [H, n_q D], "layers.i.post_norm",
+ * "layers.i.gate_up" [2I, H], "layers.i.down" [H, I].  bf16, row-major, contiguous. */
+int b200q_model_bind_weight(b200q_model_t m, const char* name, const void* dev_ptr,
+                            int64_t rows, int64_t cols);
+/* kv: [L][num_blocks][2][n_kv][block_size][D] bf16, zero-initialised by the caller */
+int b200q_model_bind_kv(b200q_model_t m, void* dev_ptr, int64_t num_blocks);
+/* cos_sin: bf16 [max_pos][D] */
+int b200q_model_bind_rope(b200q_model_t m, const void* dev_ptr);
+/* bytes needed for activations at cfg.max_tokens; caller allocates and binds */
+int64_t b200q_model_workspace_bytes(const b200q_model_config* cfg);
+int b200q_model_bind_workspace(b200q_model_t m, void* dev_ptr, int64_t bytes);
+int b200q_model_forward(b200q_model_t m, const b200q_batch* batch, void* stream);
+/* debugging / parity: copy the bf16 logits of the last forward ([n_sample, V]) location */
+const void* b200q_model_logits_ptr(b200q_model_t m);
+/* number of kernels launched by this library since load (gpu_launches evidence) */
+int64_t b200q_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Engine-level: continuous-batching scheduler + paged-KV block manager + step loop.
+ * Replaces AsyncLLMEngine.generate / EngineCore.step for the reference worker
+ * (ref:llmq/workers/vllm_worker.py:183-186; vllm/v1/core/sched/scheduler.py:329-340
+ * behaviour: running requests first, then waiting/prefill under a token budget, chunked
+ * prefill, preempt-by-recompute when the KV pool is exhausted).
+ * ---------------------------------------------------------------------------------- */
+
+typedef struct b200q_engine_config {
+  int32_t max_num_seqs;            /* VLLM_MAX_NUM_SEQS  (ref:llmq/core/config.py:27-32)  */
+  int32_t max_num_batched_tokens;  /* token budget per step (<= model max_tokens)          */
+  int32_t max_model_len;           /* VLLM_MAX_MODEL_LEN (ref:llmq/core/config.py:34-39)  */
+  int32_t eos_token_id;            /* -1: none                                            */
+} b200q_engine_config;
+
+typedef struct b200q_engine* b200q_engine_t;
+
+#define B200Q_FLAG_FINISHED_EOS 1
+#define B200Q_FLAG_FINISHED_LENGTH 2
+#define B200Q_FLAG_FINISHED_ABORT 4
+
+typedef struct b200q_engine_stats {
+  int64_t steps;
+  int64_t tokens_prefilled;
+  int64_t tokens_decoded;
+  int64_t preemptions;
+  int32_t running;
+  int32_t waiting;
+  int32_t free_blocks;
+  int32_t total_blocks;
+  int32_t last_step_tokens;
+  int32_t last_step_seqs;
+} b200q_engine_stats;
+
+int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b200q_engine_t* out);
+int b200q_engine_destroy(b200q_engine_t e);
+/* prompt ids are copied.  Returns B200Q_EINVAL if n_prompt + 1 > max_model_len (the worker
+ * turns that into ValueError => job dropped, ref:llmq/workers/base.py:228-235). */
+int b200q_engine_add_request(b200q_engine_t e, int64_t req_id, const int32_t* prompt_ids,
+                             int32_t n_prompt, int32_t max_new_tokens, int32_t ignore_eos);
+int b200q_engine_abort(b200q_engine_t e, int64_t req_id);
+/* 1 if any request is waiting or running */
+int b200q_engine_has_work(b200q_engine_t e);
+/* run one scheduler step + forward; writes up to cap (req_id, token, flags) events for the
+ * tokens produced this step.  cap must be >= max_num_seqs. */
+int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_tokens,
+                      int32_t* out_flags, int32_t cap, int32_t* n_out);
+int b200q_engine_get_stats(b200q_engine_t e, b200q_engine_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H_ */

@@ -1,0 +1,519 @@
+// attn.cu — paged-KV attention for the b200 worker.
+//
+// KV cache layout (per layer):  [num_blocks][2 (K,V)][n_kv][BS tokens][D] bf16, i.e. one
+// contiguous "page" of BS*D*2 bytes per (block, K|V, kv-head).  Inside a token row the 16-byte
+// chunk c lives at chunk position c ^ (token_in_block & 7).  The swizzle is applied by the
+// RoPE+KV-write kernel (elementwise.cu), so a page can be pulled into shared memory with ONE
+// 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) of exactly the valid rows and then be read
+// with ldmatrix without bank conflicts — the block-table gather is done by the TMA engine, no
+// thread touches KV bytes in flight.
+//
+// Decode  (K7): one CTA per (sequence, kv-head).  4 warps split the sequence's pages
+//   round-robin; every warp owns a private 3-stage ring (K page + V page per stage) fed by its
+//   own bulk copies, keeps an online-softmax state (m, l, O[G x D]) for the G query heads of
+//   the GQA group in registers, and the 4 partial states are merged through shared memory.
+//   QK^T and PV run on mma.sync m16n8k16 (rows 0..G-1 of the 16-row tile are the G heads);
+//   the kernel is HBM-bound: algorithmic bytes = ctx * D * 2 (K,V) * 2 B per (seq, kv-head).
+// Prefill (K6): one CTA per (q-tile of <=16 consecutive prompt tokens, kv-head).  G consumer
+//   warps (one per query head of the group) share a 4-stage page ring filled by a producer
+//   warp; causal masking by absolute position; K/V are read back from the paged cache, so
+//   chunked prefill over an existing context needs no special case.
+#include "common.cuh"
+
+namespace b200q {
+
+constexpr int DEC_WARPS = 4;
+constexpr int DEC_STAGES = 3;
+constexpr int PF_STAGES = 4;
+
+template <int D, int BS>
+struct Geo {
+  static constexpr int CPR = D / 8;            // 16 B chunks per token row
+  static constexpr int ROW_BYTES = D * 2;
+  static constexpr int PAGE_BYTES = BS * D * 2;
+  static constexpr int NT = BS / 8;            // 8-token n-tiles per page
+  static constexpr int KS = D / 16;            // k-steps of QK^T
+  static constexpr int ND = D / 8;             // 8-dim n-tiles of O
+};
+
+// S[nt] (16 x 8 tokens) = Q(16 x D) . K_page^T for all n-tiles of one page.
+template <int D, int BS, bool kFullRows>
+__device__ __forceinline__ void qk_page(uint32_t k_s, const uint32_t (&qa)[D / 16][4],
+                                        float (&s)[BS / 8][4], int lane) {
+  using G_ = Geo<D, BS>;
+#pragma unroll
+  for (int nt = 0; nt < G_::NT; ++nt) {
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    const int token = nt * 8 + (lane & 7);
+    const uint32_t row_addr = k_s + token * G_::ROW_BYTES;
+#pragma unroll
+    for (int j = 0; j < D / 32; ++j) {
+      const int chunk = 4 * j + (lane >> 3);
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(row_addr + ((chunk ^ (token & 7)) << 4), b0, b1, b2, b3);
+      if (kFullRows) {
+        mma_bf16_16816(s[nt], qa[2 * j][0], qa[2 * j][1], qa[2 * j][2], qa[2 * j][3], b0, b1);
+        mma_bf16_16816(s[nt], qa[2 * j + 1][0], qa[2 * j + 1][1], qa[2 * j + 1][2],
+                       qa[2 * j + 1][3], b2, b3);
+      } else {
+        mma_bf16_16816(s[nt], qa[2 * j][0], 0u, qa[2 * j][2], 0u, b0, b1);
+        mma_bf16_16816(s[nt], qa[2 * j + 1][0], 0u, qa[2 * j + 1][2], 0u, b2, b3);
+      }
+    }
+  }
+}
+
+// O(16 x D) += P(16 x BS) . V_page(BS x D); P given as fp32 accumulator fragments.
+template <int D, int BS, bool kFullRows>
+__device__ __forceinline__ void pv_page(uint32_t v_s, const float (&p)[BS / 8][4],
+                                        float (&o)[D / 8][4], int lane) {
+  using G_ = Geo<D, BS>;
+#pragma unroll
+  for (int kk = 0; kk < BS / 16; ++kk) {
+    const uint32_t a0 = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
+    const uint32_t a2 = pack_bf16x2(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+    uint32_t a1 = 0u, a3 = 0u;
+    if (kFullRows) {
+      a1 = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
+      a3 = pack_bf16x2(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+    }
+    const int token = kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+    const uint32_t row_addr = v_s + token * G_::ROW_BYTES;
+#pragma unroll
+    for (int nd2 = 0; nd2 < D / 16; ++nd2) {
+      const int chunk = 2 * nd2 + (lane >> 4);
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(row_addr + ((chunk ^ (token & 7)) << 4), b0, b1, b2, b3);
+      mma_bf16_16816(o[2 * nd2], a0, a1, a2, a3, b0, b1);
+      mma_bf16_16816(o[2 * nd2 + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+}
+
+// zero rows [n_valid, BS) of a V page in shared memory (whole warp), so that masked
+// probabilities (exactly 0) never meet stale NaN/Inf bit patterns in the PV mma.
+template <int D, int BS>
+__device__ __forceinline__ void zero_tail_rows(uint8_t* v_page, int n_valid, int lane) {
+  using G_ = Geo<D, BS>;
+  const int n = (BS - n_valid) * G_::CPR;
+  uint4* p = reinterpret_cast<uint4*>(v_page + n_valid * G_::ROW_BYTES);
+  for (int i = lane; i < n; i += 32) p[i] = make_uint4(0, 0, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// K7 decode
+// ------------------------------------------------------------------------------------------
+template <int D, int BS>
+struct DecSmem {
+  static constexpr int STAGE_BYTES = 2 * Geo<D, BS>::PAGE_BYTES;
+  static constexpr int RING_BYTES = DEC_WARPS * DEC_STAGES * STAGE_BYTES;
+  static constexpr int MERGE_FLOATS = DEC_WARPS * 8 * (D + 2);
+  static constexpr int TOTAL = RING_BYTES + MERGE_FLOATS * 4 + DEC_WARPS * DEC_STAGES * 8;
+};
+
+template <int D, int BS>
+__global__ void __launch_bounds__(DEC_WARPS * 32, 2)
+    decode_attn_kernel(const bf16* __restrict__ q, int q_stride, bf16* __restrict__ out,
+                       const uint8_t* __restrict__ kv_layer,
+                       const int32_t* __restrict__ block_table, int bt_stride,
+                       const int32_t* __restrict__ ctx_lens, int n_q, int n_kv, int G,
+                       float scale_log2) {
+  using G_ = Geo<D, BS>;
+  using S_ = DecSmem<D, BS>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int seq = blockIdx.x, kvh = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring = smem + warp * DEC_STAGES * S_::STAGE_BYTES;
+  float* merge = reinterpret_cast<float*>(smem + S_::RING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_::RING_BYTES + S_::MERGE_FLOATS * 4) +
+                   warp * DEC_STAGES;
+
+  const int ctx = __ldg(ctx_lens + seq);
+  const int n_pages = (ctx + BS - 1) / BS;
+  const int my_n = n_pages > warp ? (n_pages - warp + DEC_WARPS - 1) / DEC_WARPS : 0;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < DEC_STAGES; ++s) mbar_init(bars + s, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  const int32_t* bt = block_table + (long long)seq * bt_stride;
+  const long long page_stride = (long long)G_::PAGE_BYTES;  // bytes per (block,kv,head) page
+  // page address: ((blk*2 + kv) * n_kv + kvh) * PAGE_BYTES
+  int ids_base = 0;
+  int ids = (lane < my_n) ? __ldg(bt + warp + DEC_WARPS * lane) : 0;
+
+  auto issue = [&](int k) {  // whole warp calls; k = warp-local page index
+    if (k - ids_base >= 32) {
+      ids_base += 32;
+      ids = (ids_base + lane < my_n) ? __ldg(bt + warp + DEC_WARPS * (ids_base + lane)) : 0;
+    }
+    const int blk = __shfl_sync(0xffffffffu, ids, k - ids_base);
+    const int p = warp + DEC_WARPS * k;
+    const int n_valid = min(BS, ctx - p * BS);
+    const int st = k % DEC_STAGES;
+    uint8_t* ks = ring + st * S_::STAGE_BYTES;
+    uint8_t* vs = ks + G_::PAGE_BYTES;
+    if (n_valid < BS) {
+      zero_tail_rows<D, BS>(vs, n_valid, lane);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)n_valid * G_::ROW_BYTES;
+      const uint8_t* kp = kv_layer + (((long long)blk * 2 + 0) * n_kv + kvh) * page_stride;
+      const uint8_t* vp = kv_layer + (((long long)blk * 2 + 1) * n_kv + kvh) * page_stride;
+      mbar_expect_tx(bars + st, 2 * bytes);
+      tma_bulk_g2s(ks, kp, bytes, bars + st);
+      tma_bulk_g2s(vs, vp, bytes, bars + st);
+    }
+  };
+
+  const int n_pro = my_n < DEC_STAGES ? my_n : DEC_STAGES;
+  for (int k = 0; k < n_pro; ++k) issue(k);
+
+  // Q fragments: rows 0..G-1 of the 16-row tile are the G query heads of this kv head
+  uint32_t qa[D / 16][4];
+  {
+    const int r = lane >> 2, cq = (lane & 3) * 2;
+    const bf16* qrow = q + (long long)seq * q_stride + (long long)(kvh * G + r) * D;
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+      qa[ks][0] = r < G ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + cq) : 0u;
+      qa[ks][2] = r < G ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + cq) : 0u;
+      qa[ks][1] = 0u;
+      qa[ks][3] = 0u;
+    }
+  }
+
+  float o[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m = -INFINITY, l = 0.f;
+
+  for (int k = 0; k < my_n; ++k) {
+    const int st = k % DEC_STAGES;
+    const uint32_t phase = (uint32_t)(k / DEC_STAGES) & 1u;
+    mbar_wait(bars + st, phase);
+    const int p = warp + DEC_WARPS * k;
+    const int n_valid = min(BS, ctx - p * BS);
+    const uint32_t k_s = smem_u32(ring + st * S_::STAGE_BYTES);
+    const uint32_t v_s = k_s + G_::PAGE_BYTES;
+
+    float s[BS / 8][4];
+    qk_page<D, BS, false>(k_s, qa, s, lane);
+
+    float mx = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < G_::NT; ++nt) {
+      const int t0 = nt * 8 + (lane & 3) * 2;
+      s[nt][0] = (t0 < n_valid) ? s[nt][0] * scale_log2 : -INFINITY;
+      s[nt][1] = (t0 + 1 < n_valid) ? s[nt][1] * scale_log2 : -INFINITY;
+      mx = fmaxf(mx, fmaxf(s[nt][0], s[nt][1]));
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m, mx);  // finite: every page has >= 1 valid token
+    const float alpha = exp2f(m - m_new);
+    float psum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < G_::NT; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - m_new);
+      s[nt][1] = exp2f(s[nt][1] - m_new);
+      s[nt][2] = 0.f;
+      s[nt][3] = 0.f;
+      psum += s[nt][0] + s[nt][1];
+    }
+    l = l * alpha + psum;
+    m = m_new;
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      o[i][0] *= alpha;
+      o[i][1] *= alpha;
+    }
+    pv_page<D, BS, false>(v_s, s, o, lane);
+    __syncwarp();
+    if (k + DEC_STAGES < my_n) issue(k + DEC_STAGES);
+  }
+
+  // ---- merge the 4 per-warp partial states ----
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  {
+    const int r = lane >> 2;
+    float* mo = merge + (warp * 8 + r) * (D + 2);
+    if (r < G) {
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        mo[i * 8 + (lane & 3) * 2] = o[i][0];
+        mo[i * 8 + (lane & 3) * 2 + 1] = o[i][1];
+      }
+      if ((lane & 3) == 0) {
+        mo[D] = m;
+        mo[D + 1] = l;
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < G * D; idx += DEC_WARPS * 32) {
+    const int r = idx / D, d = idx % D;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) M = fmaxf(M, merge[(w * 8 + r) * (D + 2) + D]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) {
+      const float* mo = merge + (w * 8 + r) * (D + 2);
+      const float wgt = (mo[D] == -INFINITY) ? 0.f : exp2f(mo[D] - M);
+      num += wgt * mo[d];
+      den += wgt * mo[D + 1];
+    }
+    const float v = den > 0.f ? num / den : 0.f;
+    out[(long long)seq * n_q * D + (long long)(kvh * G + r) * D + d] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6 prefill
+// ------------------------------------------------------------------------------------------
+template <int D, int BS>
+struct PfSmem {
+  static constexpr int STAGE_BYTES = 2 * Geo<D, BS>::PAGE_BYTES;
+  static constexpr int RING_BYTES = PF_STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = RING_BYTES + 2 * PF_STAGES * 8;
+};
+
+template <int D, int BS>
+__global__ void __launch_bounds__(9 * 32)
+    prefill_attn_kernel(const bf16* __restrict__ q, int q_stride, bf16* __restrict__ out,
+                        const uint8_t* __restrict__ kv_layer,
+                        const int32_t* __restrict__ block_table, int bt_stride,
+                        const int4* __restrict__ tiles, int n_q, int n_kv, int G,
+                        float scale_log2) {
+  using G_ = Geo<D, BS>;
+  using S_ = PfSmem<D, BS>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S_::RING_BYTES);
+  uint64_t* empty = full + PF_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kvh = blockIdx.y;
+  const int4 tile = __ldg(tiles + blockIdx.x);
+  const int bt_row = tile.x, row0 = tile.y, n_rows = tile.z, pos0 = tile.w;
+  const int total_kv = pos0 + n_rows;  // keys 0 .. pos0+n_rows-1 are visible to this tile
+  const int n_pages = (total_kv + BS - 1) / BS;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < PF_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, G);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == G) {
+    // ===== producer warp: TMA page gather through the block table =====
+    const int32_t* bt = block_table + (long long)bt_row * bt_stride;
+    for (int p = 0; p < n_pages; ++p) {
+      const int st = p % PF_STAGES;
+      if (p >= PF_STAGES) mbar_wait(empty + st, (uint32_t)((p / PF_STAGES) - 1) & 1u);
+      const int n_valid = min(BS, total_kv - p * BS);
+      uint8_t* ks = smem + st * S_::STAGE_BYTES;
+      uint8_t* vs = ks + G_::PAGE_BYTES;
+      if (n_valid < BS) {
+        zero_tail_rows<D, BS>(vs, n_valid, lane);
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const int blk = __ldg(bt + p);
+        const uint32_t bytes = (uint32_t)n_valid * G_::ROW_BYTES;
+        const uint8_t* kp =
+            kv_layer + (((long long)blk * 2 + 0) * n_kv + kvh) * (long long)G_::PAGE_BYTES;
+        const uint8_t* vp =
+            kv_layer + (((long long)blk * 2 + 1) * n_kv + kvh) * (long long)G_::PAGE_BYTES;
+        mbar_expect_tx(full + st, 2 * bytes);
+        tma_bulk_g2s(ks, kp, bytes, full + st);
+        tma_bulk_g2s(vs, vp, bytes, full + st);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  if (warp > G) return;
+
+  // ===== consumer warp `warp` = query head kvh*G + warp; 16 rows = 16 tokens of the tile =====
+  const int head = kvh * G + warp;
+  const int r = lane >> 2, cq = (lane & 3) * 2;
+  uint32_t qa[D / 16][4];
+  {
+    const bf16* q0 = q + (long long)(row0 + r) * q_stride + (long long)head * D;
+    const bf16* q1 = q + (long long)(row0 + r + 8) * q_stride + (long long)head * D;
+    const bool v0 = r < n_rows, v1 = r + 8 < n_rows;
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+      qa[ks][0] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + cq) : 0u;
+      qa[ks][1] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + cq) : 0u;
+      qa[ks][2] = v0 ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8 + cq) : 0u;
+      qa[ks][3] = v1 ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8 + cq) : 0u;
+    }
+  }
+  float o[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  // last visible key index per row (causal), clamped to the keys that exist
+  const int lim0 = min(pos0 + r, total_kv - 1), lim1 = min(pos0 + r + 8, total_kv - 1);
+
+  for (int p = 0; p < n_pages; ++p) {
+    const int st = p % PF_STAGES;
+    mbar_wait(full + st, (uint32_t)(p / PF_STAGES) & 1u);
+    const uint32_t k_s = smem_u32(smem + st * S_::STAGE_BYTES);
+    const uint32_t v_s = k_s + G_::PAGE_BYTES;
+    float s[BS / 8][4];
+    qk_page<D, BS, true>(k_s, qa, s, lane);
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < G_::NT; ++nt) {
+      const int j = p * BS + nt * 8 + cq;
+      s[nt][0] = (j <= lim0) ? s[nt][0] * scale_log2 : -INFINITY;
+      s[nt][1] = (j + 1 <= lim0) ? s[nt][1] * scale_log2 : -INFINITY;
+      s[nt][2] = (j <= lim1) ? s[nt][2] * scale_log2 : -INFINITY;
+      s[nt][3] = (j + 1 <= lim1) ? s[nt][3] * scale_log2 : -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    // key 0 is visible to every row, so after page 0 both maxima are finite
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < G_::NT; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - mn0);
+      s[nt][1] = exp2f(s[nt][1] - mn0);
+      s[nt][2] = exp2f(s[nt][2] - mn1);
+      s[nt][3] = exp2f(s[nt][3] - mn1);
+      ps0 += s[nt][0] + s[nt][1];
+      ps1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * a0 + ps0;
+    l1 = l1 * a1 + ps1;
+    m0 = mn0;
+    m1 = mn1;
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      o[i][0] *= a0;
+      o[i][1] *= a0;
+      o[i][2] *= a1;
+      o[i][3] *= a1;
+    }
+    pv_page<D, BS, true>(v_s, s, o, lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + st);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+  bf16* o0 = out + (long long)(row0 + r) * n_q * D + (long long)head * D;
+  bf16* o1 = out + (long long)(row0 + r + 8) * n_q * D + (long long)head * D;
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) {
+    if (r < n_rows)
+      *reinterpret_cast<uint32_t*>(o0 + i * 8 + cq) = pack_bf16x2(o[i][0] * i0, o[i][1] * i0);
+    if (r + 8 < n_rows)
+      *reinterpret_cast<uint32_t*>(o1 + i * 8 + cq) = pack_bf16x2(o[i][2] * i1, o[i][3] * i1);
+  }
+}
+
+template <int D, int BS>
+static int launch_decode(const void* q, int q_stride, void* out, const void* kv,
+                         const int32_t* bt, int bt_stride, const int32_t* ctx, int n_seqs, int n_q,
+                         int n_kv, float scale, cudaStream_t st) {
+  using S_ = DecSmem<D, BS>;
+  auto kern = decode_attn_kernel<D, BS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid(n_seqs, n_kv);
+  kern<<<grid, DEC_WARPS * 32, S_::TOTAL, st>>>((const bf16*)q, q_stride, (bf16*)out,
+                                                (const uint8_t*)kv, bt, bt_stride, ctx, n_q, n_kv,
+                                                n_q / n_kv, scale * 1.4426950408889634f);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
+template <int D, int BS>
+static int launch_prefill(const void* q, int q_stride, void* out, const void* kv,
+                          const int32_t* bt, int bt_stride, const int32_t* tiles, int n_tiles,
+                          int n_q, int n_kv, float scale, cudaStream_t st) {
+  using S_ = PfSmem<D, BS>;
+  auto kern = prefill_attn_kernel<D, BS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::TOTAL));
+    attr_set = true;
+  }
+  const int G = n_q / n_kv;
+  dim3 grid(n_tiles, n_kv);
+  kern<<<grid, (G + 1) * 32, S_::TOTAL, st>>>((const bf16*)q, q_stride, (bf16*)out,
+                                              (const uint8_t*)kv, bt, bt_stride,
+                                              (const int4*)tiles, n_q, n_kv, G,
+                                              scale * 1.4426950408889634f);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" {
+
+int b200q_decode_attn(const void* q, int q_stride, void* out, const void* kv_layer,
+                      const int32_t* block_table, int bt_stride, const int32_t* ctx_lens,
+                      int n_seqs, int n_q, int n_kv, int D, int block_size, float scale,
+                      void* stream) {
+  B200Q_CHECK_ARG(n_seqs >= 0 && n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= 8,
+                  "decode_attn: unsupported heads n_q=%d n_kv=%d (GQA group must be <= 8)", n_q,
+                  n_kv);
+  B200Q_CHECK_ARG(block_size == 16 && (D == 64 || D == 128),
+                  "decode_attn: unsupported D=%d block_size=%d (D in {64,128}, block 16)", D,
+                  block_size);
+  if (n_seqs == 0) return B200Q_OK;
+  cudaStream_t st = as_stream(stream);
+  if (D == 128)
+    return launch_decode<128, 16>(q, q_stride, out, kv_layer, block_table, bt_stride, ctx_lens,
+                                  n_seqs, n_q, n_kv, scale, st);
+  return launch_decode<64, 16>(q, q_stride, out, kv_layer, block_table, bt_stride, ctx_lens,
+                               n_seqs, n_q, n_kv, scale, st);
+}
+
+int b200q_prefill_attn(const void* q, int q_stride, void* out, const void* kv_layer,
+                       const int32_t* block_table, int bt_stride, const int32_t* tiles,
+                       int n_tiles, int n_q, int n_kv, int D, int block_size, float scale,
+                       void* stream) {
+  B200Q_CHECK_ARG(n_tiles >= 0 && n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= 8,
+                  "prefill_attn: unsupported heads n_q=%d n_kv=%d (GQA group must be <= 8)", n_q,
+                  n_kv);
+  B200Q_CHECK_ARG(block_size == 16 && (D == 64 || D == 128),
+                  "prefill_attn: unsupported D=%d block_size=%d (D in {64,128}, block 16)", D,
+                  block_size);
+  if (n_tiles == 0) return B200Q_OK;
+  cudaStream_t st = as_stream(stream);
+  if (D == 128)
+    return launch_prefill<128, 16>(q, q_stride, out, kv_layer, block_table, bt_stride, tiles,
+                                   n_tiles, n_q, n_kv, scale, st);
+  return launch_prefill<64, 16>(q, q_stride, out, kv_layer, block_table, bt_stride, tiles,
+                                n_tiles, n_q, n_kv, scale, st);
+}
+
+}  // extern "C"

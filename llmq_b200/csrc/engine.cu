@@ -1,0 +1,403 @@
+// engine.cu — continuous-batching scheduler, paged-KV block manager and step loop.
+//
+// Replaces the part of vLLM that sits behind `engine.generate` in the reference worker
+// (ref:llmq/workers/vllm_worker.py:183-186): EngineCore.step = Scheduler.schedule() +
+// execute_model + update_from_output.  The *behaviour* mirrored from
+// vllm/v1/core/sched/scheduler.py:329-340 is: there is no separate prefill/decode phase — every
+// step hands each request `num_tokens - num_computed_tokens` new tokens under a global token
+// budget; RUNNING requests are served first, then WAITING ones (FIFO), long prompts are chunked
+// by the budget, and when the KV pool is exhausted the most recently admitted running request
+// is preempted and later recomputed from its tokens.
+//
+// The host side is deliberately plain C++: per step it fills ONE pinned staging buffer with all
+// int32 metadata (token ids, positions, slot mapping, context lengths, prefill q-tiles, sample
+// rows, block table), ships it with one H2D copy, runs the forward on the engine's stream and
+// reads back the sampled ids with one D2H copy.
+#include <algorithm>
+#include <deque>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200q {
+const b200q_model_config& model_cfg(b200q_model_t m);
+int64_t model_num_blocks(b200q_model_t m);
+}  // namespace b200q
+
+using namespace b200q;
+
+namespace {
+
+struct Request {
+  int64_t id;
+  std::vector<int32_t> tokens;  // prompt + generated
+  int32_t n_prompt;
+  int32_t n_computed = 0;       // tokens whose KV is in the cache
+  int32_t n_generated = 0;
+  int32_t max_new;
+  bool ignore_eos;
+  std::vector<int32_t> blocks;
+  int32_t n_sched = 0;          // tokens scheduled in the current step
+  int32_t sample_slot = -1;     // index into out_ids for this step, or -1
+};
+
+}  // namespace
+
+struct b200q_engine {
+  b200q_model_t model;
+  b200q_engine_config cfg;
+  b200q_model_config mcfg;
+  int block_size;
+  int max_blocks_per_seq;
+  cudaStream_t stream = nullptr;
+
+  std::unordered_map<int64_t, Request*> by_id;
+  std::deque<Request*> waiting;
+  std::vector<Request*> running;
+  std::vector<int32_t> free_blocks;
+  int32_t total_blocks = 0;
+
+  int32_t* h_meta = nullptr;  // pinned
+  int32_t* d_meta = nullptr;
+  int64_t meta_cap = 0;       // int32 elements
+  int32_t* h_out = nullptr;   // pinned
+  int32_t* d_out = nullptr;
+
+  b200q_engine_stats stats{};
+};
+
+static void free_request_blocks(b200q_engine* e, Request* r) {
+  for (int32_t b : r->blocks) e->free_blocks.push_back(b);
+  r->blocks.clear();
+}
+
+static bool ensure_blocks(b200q_engine* e, Request* r, int n_tokens_total) {
+  const int need = (n_tokens_total + e->block_size - 1) / e->block_size;
+  const int have = (int)r->blocks.size();
+  if (need <= have) return true;
+  if ((int)e->free_blocks.size() < need - have) return false;
+  for (int i = have; i < need; ++i) {
+    r->blocks.push_back(e->free_blocks.back());
+    e->free_blocks.pop_back();
+  }
+  return true;
+}
+
+extern "C" {
+
+int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b200q_engine_t* out) {
+  B200Q_CHECK_ARG(model && cfg && out, "engine_create: null argument");
+  const b200q_model_config& mc = model_cfg(model);
+  B200Q_CHECK_ARG(cfg->max_num_seqs > 0 && cfg->max_num_seqs <= mc.max_seqs,
+                  "max_num_seqs=%d must be in [1, model max_seqs=%d]", cfg->max_num_seqs,
+                  mc.max_seqs);
+  B200Q_CHECK_ARG(cfg->max_num_batched_tokens > 0 && cfg->max_num_batched_tokens <= mc.max_tokens,
+                  "max_num_batched_tokens=%d must be in [1, model max_tokens=%d]",
+                  cfg->max_num_batched_tokens, mc.max_tokens);
+  B200Q_CHECK_ARG(cfg->max_model_len > 1 && cfg->max_model_len <= mc.max_pos,
+                  "max_model_len=%d must be in [2, rope table rows=%d]", cfg->max_model_len,
+                  mc.max_pos);
+  B200Q_CHECK_ARG(model_num_blocks(model) > 0, "engine_create: bind the KV cache first");
+  b200q_engine* e = new b200q_engine();
+  e->model = model;
+  e->cfg = *cfg;
+  e->mcfg = mc;
+  e->block_size = mc.block_size;
+  e->max_blocks_per_seq = (cfg->max_model_len + mc.block_size - 1) / mc.block_size;
+  e->total_blocks = (int32_t)std::min<int64_t>(model_num_blocks(model), 0x7fffffff);
+  e->free_blocks.reserve(e->total_blocks);
+  for (int32_t b = e->total_blocks - 1; b >= 0; --b) e->free_blocks.push_back(b);
+
+  const int64_t T = cfg->max_num_batched_tokens, S = cfg->max_num_seqs;
+  // token_ids, positions, slot_mapping [T each]; ctx_lens [S]; sample_rows [S];
+  // tiles [4 * (T/16 + S)]; block table [S * max_blocks_per_seq]
+  e->meta_cap = 3 * T + 2 * S + 4 * (T / 16 + S + 2) +
+                S * (int64_t)((e->max_blocks_per_seq + 7) & ~7) + 64;
+  cudaError_t ce;
+  if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (ce = cudaMallocHost(&e->h_meta, e->meta_cap * 4)) != cudaSuccess ||
+      (ce = cudaMalloc(&e->d_meta, e->meta_cap * 4)) != cudaSuccess ||
+      (ce = cudaMallocHost(&e->h_out, S * 4)) != cudaSuccess ||
+      (ce = cudaMalloc(&e->d_out, S * 4)) != cudaSuccess) {
+    set_error("engine_create: CUDA allocation failed: %s", cudaGetErrorString(ce));
+    b200q_engine_destroy(e);
+    return B200Q_ECUDA;
+  }
+  // weights / KV were produced on other streams (torch); make them visible before first use
+  cudaDeviceSynchronize();
+  *out = e;
+  return B200Q_OK;
+}
+
+int b200q_engine_destroy(b200q_engine_t e) {
+  if (!e) return B200Q_OK;
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (auto& kv : e->by_id) delete kv.second;
+  if (e->h_meta) cudaFreeHost(e->h_meta);
+  if (e->d_meta) cudaFree(e->d_meta);
+  if (e->h_out) cudaFreeHost(e->h_out);
+  if (e->d_out) cudaFree(e->d_out);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return B200Q_OK;
+}
+
+int b200q_engine_add_request(b200q_engine_t e, int64_t req_id, const int32_t* prompt_ids,
+                             int32_t n_prompt, int32_t max_new_tokens, int32_t ignore_eos) {
+  B200Q_CHECK_ARG(e && prompt_ids, "add_request: null argument");
+  B200Q_CHECK_ARG(n_prompt >= 1, "add_request: empty prompt");
+  B200Q_CHECK_ARG(n_prompt < e->cfg.max_model_len,
+                  "prompt of %d tokens does not fit max_model_len=%d", n_prompt,
+                  e->cfg.max_model_len);
+  B200Q_CHECK_ARG(max_new_tokens >= 1, "add_request: max_new_tokens must be >= 1");
+  B200Q_CHECK_ARG(e->by_id.find(req_id) == e->by_id.end(), "add_request: duplicate request id %lld",
+                  (long long)req_id);
+  for (int i = 0; i < n_prompt; ++i)
+    B200Q_CHECK_ARG(prompt_ids[i] >= 0 && prompt_ids[i] < e->mcfg.vocab,
+                    "add_request: token id %d out of range at %d", prompt_ids[i], i);
+  // a request must be able to run alone: its full length has to fit the KV pool
+  const int max_total = std::min(n_prompt + max_new_tokens, e->cfg.max_model_len);
+  B200Q_CHECK_ARG((max_total + e->block_size - 1) / e->block_size <= e->total_blocks,
+                  "request of up to %d tokens cannot fit the KV pool (%d blocks)", max_total,
+                  e->total_blocks);
+  Request* r = new Request();
+  r->id = req_id;
+  r->tokens.assign(prompt_ids, prompt_ids + n_prompt);
+  r->n_prompt = n_prompt;
+  r->max_new = std::min(max_new_tokens, e->cfg.max_model_len - n_prompt);
+  r->ignore_eos = ignore_eos != 0;
+  e->by_id[req_id] = r;
+  e->waiting.push_back(r);
+  return B200Q_OK;
+}
+
+int b200q_engine_abort(b200q_engine_t e, int64_t req_id) {
+  B200Q_CHECK_ARG(e, "abort: null engine");
+  auto it = e->by_id.find(req_id);
+  if (it == e->by_id.end()) return B200Q_OK;
+  Request* r = it->second;
+  auto w = std::find(e->waiting.begin(), e->waiting.end(), r);
+  if (w != e->waiting.end()) e->waiting.erase(w);
+  auto ru = std::find(e->running.begin(), e->running.end(), r);
+  if (ru != e->running.end()) e->running.erase(ru);
+  free_request_blocks(e, r);
+  e->by_id.erase(it);
+  delete r;
+  return B200Q_OK;
+}
+
+int b200q_engine_has_work(b200q_engine_t e) {
+  return e && (!e->waiting.empty() || !e->running.empty()) ? 1 : 0;
+}
+
+int b200q_engine_get_stats(b200q_engine_t e, b200q_engine_stats* out) {
+  B200Q_CHECK_ARG(e && out, "get_stats: null argument");
+  e->stats.running = (int32_t)e->running.size();
+  e->stats.waiting = (int32_t)e->waiting.size();
+  e->stats.free_blocks = (int32_t)e->free_blocks.size();
+  e->stats.total_blocks = e->total_blocks;
+  *out = e->stats;
+  return B200Q_OK;
+}
+
+int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_tokens,
+                      int32_t* out_flags, int32_t cap, int32_t* n_out) {
+  B200Q_CHECK_ARG(e && out_req_ids && out_tokens && out_flags && n_out, "step: null argument");
+  B200Q_CHECK_ARG(cap >= e->cfg.max_num_seqs, "step: event capacity %d < max_num_seqs %d", cap,
+                  e->cfg.max_num_seqs);
+  *n_out = 0;
+  int budget = e->cfg.max_num_batched_tokens;
+
+  // ---- 1. running requests first ----
+  std::vector<Request*> sched;
+  sched.reserve(e->running.size() + 16);
+  for (size_t i = 0; i < e->running.size();) {
+    Request* r = e->running[i];
+    int n_new = (int)r->tokens.size() - r->n_computed;
+    n_new = std::min(n_new, budget);
+    if (n_new <= 0) {
+      r->n_sched = 0;
+      ++i;
+      continue;
+    }
+    bool ok = ensure_blocks(e, r, r->n_computed + n_new);
+    while (!ok) {
+      // preempt the most recently admitted running request (recompute later)
+      Request* victim = e->running.back();
+      e->running.pop_back();
+      free_request_blocks(e, victim);
+      victim->n_computed = 0;
+      victim->n_sched = 0;
+      e->waiting.push_front(victim);
+      e->stats.preemptions++;
+      auto sit = std::find(sched.begin(), sched.end(), victim);
+      if (sit != sched.end()) {  // (cannot happen: victims are behind us in `running`)
+        budget += victim->n_sched;
+        sched.erase(sit);
+      }
+      if (victim == r) break;
+      ok = ensure_blocks(e, r, r->n_computed + n_new);
+    }
+    if (!ok) break;  // r itself was preempted; everything after it is gone too
+    r->n_sched = n_new;
+    budget -= n_new;
+    sched.push_back(r);
+    ++i;
+  }
+
+  // ---- 2. admit waiting requests (FIFO) ----
+  while (budget > 0 && !e->waiting.empty() && (int)e->running.size() < e->cfg.max_num_seqs) {
+    Request* r = e->waiting.front();
+    int n_new = std::min((int)r->tokens.size() - r->n_computed, budget);
+    if (!ensure_blocks(e, r, r->n_computed + n_new)) break;
+    e->waiting.pop_front();
+    e->running.push_back(r);
+    r->n_sched = n_new;
+    budget -= n_new;
+    sched.push_back(r);
+  }
+
+  if (sched.empty()) {
+    if (!e->waiting.empty() && e->running.empty()) {
+      set_error("scheduler stalled: a waiting request cannot be admitted (KV pool too small)");
+      return B200Q_ENOMEM;
+    }
+    return B200Q_OK;
+  }
+
+  // ---- 3. order: single-token pieces (decode) first, then multi-token prefill chunks ----
+  std::stable_partition(sched.begin(), sched.end(), [](Request* r) { return r->n_sched == 1; });
+  int n_dec = 0, T = 0, max_blocks = 1;
+  for (Request* r : sched) {
+    if (r->n_sched == 1) ++n_dec;
+    T += r->n_sched;
+    max_blocks = std::max(max_blocks, (int)r->blocks.size());
+  }
+  const int n_rows = (int)sched.size();
+  const int bt_stride = (max_blocks + 7) & ~7;
+
+  int32_t* tok = e->h_meta;
+  int32_t* pos = tok + T;
+  int32_t* slot = pos + T;
+  int32_t* ctx = slot + T;
+  int32_t* srows = ctx + n_dec;
+  int32_t* tiles = srows + n_rows;  // reserve n_rows sample slots
+  tiles += (4 - ((tiles - e->h_meta) & 3)) & 3;  // the prefill kernel reads tiles as int4
+  int n_tiles = 0, n_sample = 0, row = 0;
+  // count tiles first to place the block table after them
+  for (Request* r : sched)
+    if (r->n_sched > 1) n_tiles += (r->n_sched + 15) / 16;
+  int32_t* btab = tiles + 4 * n_tiles;
+  // keep the block table 16-byte aligned for tidy copies
+  btab += (4 - ((btab - e->h_meta) & 3)) & 3;
+  const int64_t used = (btab - e->h_meta) + (int64_t)n_rows * bt_stride;
+  if (used > e->meta_cap) {
+    set_error("step: metadata buffer overflow (%lld > %lld)", (long long)used,
+              (long long)e->meta_cap);
+    return B200Q_ENOMEM;
+  }
+  int ti = 0;
+  for (int ri = 0; ri < n_rows; ++ri) {
+    Request* r = sched[ri];
+    const int bs = e->block_size;
+    for (int j = 0; j < r->n_sched; ++j) {
+      const int p = r->n_computed + j;
+      tok[row + j] = r->tokens[p];
+      pos[row + j] = p;
+      slot[row + j] = r->blocks[p / bs] * bs + (p % bs);
+    }
+    if (r->n_sched == 1) {
+      ctx[ri] = r->n_computed + 1;
+    } else {
+      for (int j = 0; j < r->n_sched; j += 16) {
+        tiles[4 * ti + 0] = ri;
+        tiles[4 * ti + 1] = row + j;
+        tiles[4 * ti + 2] = std::min(16, r->n_sched - j);
+        tiles[4 * ti + 3] = r->n_computed + j;
+        ++ti;
+      }
+    }
+    if (r->n_computed + r->n_sched == (int)r->tokens.size()) {
+      r->sample_slot = n_sample;
+      srows[n_sample++] = row + r->n_sched - 1;
+    } else {
+      r->sample_slot = -1;
+    }
+    int32_t* brow = btab + (int64_t)ri * bt_stride;
+    const int nb = (int)r->blocks.size();
+    for (int k = 0; k < nb; ++k) brow[k] = r->blocks[k];
+    for (int k = nb; k < bt_stride; ++k) brow[k] = 0;
+    row += r->n_sched;
+  }
+
+  cudaError_t ce = cudaMemcpyAsync(e->d_meta, e->h_meta, used * 4, cudaMemcpyHostToDevice, e->stream);
+  if (ce != cudaSuccess) {
+    set_error("step: H2D metadata copy failed: %s", cudaGetErrorString(ce));
+    return B200Q_ECUDA;
+  }
+  b200q_batch b;
+  b.T = T;
+  b.n_dec = n_dec;
+  b.n_tiles = n_tiles;
+  b.n_sample = n_sample;
+  b.bt_stride = bt_stride;
+  b.token_ids = e->d_meta + (tok - e->h_meta);
+  b.positions = e->d_meta + (pos - e->h_meta);
+  b.slot_mapping = e->d_meta + (slot - e->h_meta);
+  b.ctx_lens = e->d_meta + (ctx - e->h_meta);
+  b.sample_rows = e->d_meta + (srows - e->h_meta);
+  b.tiles = e->d_meta + (tiles - e->h_meta);
+  b.block_table = e->d_meta + (btab - e->h_meta);
+  b.out_ids = e->d_out;
+  int rc = b200q_model_forward(e->model, &b, e->stream);
+  if (rc) return rc;
+  if (n_sample > 0) {
+    ce = cudaMemcpyAsync(e->h_out, e->d_out, (size_t)n_sample * 4, cudaMemcpyDeviceToHost, e->stream);
+    if (ce != cudaSuccess) {
+      set_error("step: D2H copy failed: %s", cudaGetErrorString(ce));
+      return B200Q_ECUDA;
+    }
+  }
+  ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) {
+    set_error("step: forward failed: %s", cudaGetErrorString(ce));
+    return B200Q_ECUDA;
+  }
+
+  // ---- 4. update from output ----
+  e->stats.steps++;
+  e->stats.last_step_tokens = T;
+  e->stats.last_step_seqs = n_rows;
+  int n_ev = 0;
+  for (Request* r : sched) {
+    const bool was_decode = r->n_computed >= r->n_prompt;
+    r->n_computed += r->n_sched;
+    if (was_decode) e->stats.tokens_decoded += r->n_sched;
+    else e->stats.tokens_prefilled += r->n_sched;
+    r->n_sched = 0;
+    if (r->sample_slot < 0) continue;
+    const int32_t t = e->h_out[r->sample_slot];
+    r->tokens.push_back(t);
+    r->n_generated++;
+    int flags = 0;
+    if (!r->ignore_eos && e->cfg.eos_token_id >= 0 && t == e->cfg.eos_token_id)
+      flags = B200Q_FLAG_FINISHED_EOS;
+    else if (r->n_generated >= r->max_new || (int)r->tokens.size() >= e->cfg.max_model_len)
+      flags = B200Q_FLAG_FINISHED_LENGTH;
+    out_req_ids[n_ev] = r->id;
+    out_tokens[n_ev] = t;
+    out_flags[n_ev] = flags;
+    ++n_ev;
+    if (flags) {
+      free_request_blocks(e, r);
+      e->running.erase(std::find(e->running.begin(), e->running.end(), r));
+      e->by_id.erase(r->id);
+      delete r;
+    }
+  }
+  *n_out = n_ev;
+  return B200Q_OK;
+}
+
+}  // extern "C"

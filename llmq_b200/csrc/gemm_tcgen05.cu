@@ -1,0 +1,410 @@
+// gemm_tcgen05.cu — C[M,N] = A[M,K] . W[N,K]^T (bf16 in, fp32 accumulate in TMEM, bf16 out)
+// for the QKV / O / gate_up / down / LM-head projections (SURVEY.md §2.1 K3,K8,K9,K11,K12),
+// the only dense contractions of the hot path.  Hand-written for sm_100a:
+//
+//   * persistent, warp-specialised CTA (192 threads): warp 0 = TMA producer (UTMALDG, 128B
+//     swizzle), warp 1 = tcgen05.mma issuer (one lane; also owns the TMEM allocation),
+//     warps 2-5 = epilogue (tcgen05.ld -> bf16 -> global).
+//   * tile 128 x BN x 64 (BN in {64,128,256}), smem ring of 4..8 stages (<= 192 KB), operands
+//     K-major in shared memory exactly as TMA lays them down (SWIZZLE_128B), described to the
+//     tensor core by UMMA shared-memory descriptors; UMMA shape M=128, N=BN, K=16.
+//   * two TMEM accumulator stages (2 x BN fp32 columns): the MMA warp runs tile i+1 while the
+//     epilogue warps drain tile i.
+//   * tile order is m-fastest so concurrently running CTAs share one weight tile through L2
+//     (weights stream from HBM exactly once; activations are L2-resident).
+//
+// Roofline: decode-sized M is HBM-bound on the weight stream (N*K*2 bytes), M >= ~256 is
+// tensor-bound (2*M*N*K flops against the measured bf16 peak).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace b200q {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle span
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BUDGET = 196608;  // ring bytes
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = GEMM_SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : GEMM_SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---- tcgen05 PTX wrappers ------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46) version[46,48)
+//  layout_type[61,64)).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);        // start address, 16 B units
+  d |= (uint64_t)1 << 16;                              // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                    // SBO: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(GEMM_BM >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                     const __grid_constant__ CUtensorMap tmap_b, bf16* __restrict__ C, int M,
+                     int N, int K) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = N / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = K / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tmem_full + 0, 1);
+    mbar_init(tmem_full + 1, 1);
+    mbar_init(tmem_empty + 0, 4);
+    mbar_init(tmem_empty + 1, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1u);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(full + stage, Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, kb * GEMM_BK, m_blk * GEMM_BM, full + stage);
+          tma_load_2d(sb, &tmap_b, kb * GEMM_BK, n_blk * BN, full + stage);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tmem_empty + acc, acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full + stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * 32);
+            const uint64_t bd = make_smem_desc(sb + k * 32);
+            umma_bf16(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty + stage);  // smem stage free once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(tmem_full + acc);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + quarter * 32 + lane;
+      bf16* crow = C + (long long)row * N + (long long)n_blk * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (row < M) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+            st_v4(crow + c0 + 8 * j, o);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---- host side: tensor maps + launch ---------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  long long rows, cols;
+  int box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h ^= std::hash<long long>()(k.rows * 1315423911LL + k.cols * 2654435761LL + k.box_rows) +
+         0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+// bf16 row-major [rows, cols] -> tiled map with box {64 cols, box_rows rows}, 128B swizzle
+static int get_tmap(const void* ptr, long long rows, long long cols, int box_rows,
+                    CUtensorMap* out) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{ptr, rows, cols, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return B200Q_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old / no driver)");
+    return B200Q_ECUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%lld,%lld] box_rows=%d ptr=%p", (int)r,
+              rows, cols, box_rows, ptr);
+    return B200Q_ECUDA;
+  }
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+  }
+  *out = m;
+  return B200Q_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int K,
+                       cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  int rc = get_tmap(A, M, K, GEMM_BM, &ta);
+  if (rc) return rc;
+  rc = get_tmap(W, N, K, BN, &tb);
+  if (rc) return rc;
+  auto kern = gemm_bf16_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200Q_CUDA(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+    attr_set = true;
+  }
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
+int g_gemm_force_bn = 0;  // test hook: 0 = heuristic
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" {
+
+// test/tuning hook (not part of the reference-facing surface): force the N tile (0 = auto)
+int b200q_gemm_set_tile_n(int bn) {
+  B200Q_CHECK_ARG(bn == 0 || bn == 64 || bn == 128 || bn == 256, "gemm tile N must be 0/64/128/256");
+  g_gemm_force_bn = bn;
+  return B200Q_OK;
+}
+
+int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, void* stream) {
+  B200Q_CHECK_ARG(M >= 0 && N > 0 && K > 0 && K % GEMM_BK == 0 && N % 64 == 0,
+                  "gemm: unsupported shape M=%d N=%d K=%d (need K%%64==0, N%%64==0)", M, N, K);
+  B200Q_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+                  "gemm: operands must be 16-byte aligned");
+  if (M == 0) return B200Q_OK;
+  cudaStream_t st = as_stream(stream);
+  int bn = g_gemm_force_bn;
+  if (bn == 0) {
+    // largest N tile that still gives every SM a tile; wave count decides among candidates
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    const int sms = num_sms();
+    bn = 64;
+    if (N % 256 == 0 && (long long)m_tiles * (N / 256) >= sms) bn = 256;
+    else if (N % 128 == 0 && (long long)m_tiles * (N / 128) >= sms) bn = 128;
+    else if (N % 256 == 0 && (long long)m_tiles * (N / 64) < sms) bn = 64;
+  }
+  if (N % bn != 0) bn = (N % 128 == 0) ? 128 : 64;
+  if (bn == 256) return launch_gemm<256>(A, W, C, M, N, K, st);
+  if (bn == 128) return launch_gemm<128>(A, W, C, M, N, K, st);
+  return launch_gemm<64>(A, W, C, M, N, K, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+// model.cu — one forward step of a Llama-architecture decoder over a mixed decode+prefill
+// token batch, composed from the op-level kernels.  Replaces GPUModelRunner.execute_model for
+// LlamaForCausalLM behind the reference worker (vllm/model_executor/models/llama.py:316-333,
+// 395-431): same layer wiring and rounding points, B200-native kernels.
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace b200q;
+
+struct b200q_layer {
+  const void* input_norm = nullptr;
+  const void* qkv = nullptr;
+  const void* o = nullptr;
+  const void* post_norm = nullptr;
+  const void* gate_up = nullptr;
+  const void* down = nullptr;
+};
+
+struct b200q_model {
+  b200q_model_config cfg;
+  const void* embed = nullptr;
+  const void* final_norm = nullptr;
+  const void* lm_head = nullptr;
+  std::vector<b200q_layer> layers;
+  uint8_t* kv = nullptr;
+  int64_t num_blocks = 0;
+  const void* rope = nullptr;
+  // workspace views
+  uint8_t* ws = nullptr;
+  int64_t ws_bytes = 0;
+  bf16 *x = nullptr, *residual = nullptr, *qkv = nullptr, *attn = nullptr, *gate_up = nullptr,
+       *act = nullptr, *sel = nullptr, *logits = nullptr;
+};
+
+static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+static int64_t qkv_dim(const b200q_model_config& c) {
+  return (int64_t)(c.n_q_heads + 2 * c.n_kv_heads) * c.head_dim;
+}
+
+static int check_cfg(const b200q_model_config* c) {
+  B200Q_CHECK_ARG(c != nullptr, "model config is null");
+  B200Q_CHECK_ARG(c->hidden > 0 && c->hidden % 64 == 0 && c->hidden <= 8192,
+                  "hidden=%d unsupported (multiple of 64, <= 8192)", c->hidden);
+  B200Q_CHECK_ARG(c->head_dim == 64 || c->head_dim == 128, "head_dim=%d unsupported", c->head_dim);
+  B200Q_CHECK_ARG(c->n_kv_heads > 0 && c->n_q_heads % c->n_kv_heads == 0 &&
+                      c->n_q_heads / c->n_kv_heads <= 8,
+                  "heads n_q=%d n_kv=%d unsupported", c->n_q_heads, c->n_kv_heads);
+  B200Q_CHECK_ARG(c->intermediate > 0 && c->intermediate % 64 == 0, "intermediate=%d unsupported",
+                  c->intermediate);
+  B200Q_CHECK_ARG(c->vocab > 0 && c->vocab % 64 == 0, "vocab=%d must be a multiple of 64", c->vocab);
+  B200Q_CHECK_ARG(c->block_size == 16, "block_size=%d unsupported (16)", c->block_size);
+  B200Q_CHECK_ARG(c->n_layers > 0 && c->max_tokens > 0 && c->max_seqs > 0 && c->max_pos > 0,
+                  "bad sizes L=%d max_tokens=%d max_seqs=%d max_pos=%d", c->n_layers,
+                  c->max_tokens, c->max_seqs, c->max_pos);
+  B200Q_CHECK_ARG((c->n_q_heads * c->head_dim) % 64 == 0 && qkv_dim(*c) % 64 == 0,
+                  "projection widths must be multiples of 64");
+  return B200Q_OK;
+}
+
+extern "C" {
+
+int64_t b200q_model_workspace_bytes(const b200q_model_config* c) {
+  if (check_cfg(c) != B200Q_OK) return -1;
+  const int64_t T = c->max_tokens, S = c->max_seqs;
+  int64_t b = 0;
+  b += 2 * align256(T * c->hidden * 2);                                  // x, residual
+  b += align256(T * qkv_dim(*c) * 2);                                    // qkv
+  b += align256(T * (int64_t)c->n_q_heads * c->head_dim * 2);            // attn
+  b += align256(T * 2 * (int64_t)c->intermediate * 2);                   // gate_up
+  b += align256(T * (int64_t)c->intermediate * 2);                       // act
+  b += align256(S * (int64_t)c->hidden * 2);                             // sel
+  b += align256(S * (int64_t)c->vocab * 2);                              // logits
+  return b;
+}
+
+int b200q_model_create(const b200q_model_config* cfg, b200q_model_t* out) {
+  B200Q_CHECK_ARG(out != nullptr, "out is null");
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  rc = b200q_device_check();
+  if (rc) return rc;
+  b200q_model* m = new b200q_model();
+  m->cfg = *cfg;
+  m->layers.resize(cfg->n_layers);
+  *out = m;
+  return B200Q_OK;
+}
+
+int b200q_model_destroy(b200q_model_t m) {
+  delete m;
+  return B200Q_OK;
+}
+
+int b200q_model_bind_weight(b200q_model_t m, const char* name, const void* p, int64_t rows,
+                            int64_t cols) {
+  B200Q_CHECK_ARG(m && name && p, "bind_weight: null argument");
+  B200Q_CHECK_ARG((reinterpret_cast<uintptr_t>(p) & 15) == 0, "weight %s not 16-byte aligned", name);
+  const b200q_model_config& c = m->cfg;
+  const int64_t H = c.hidden, I = c.intermediate, QKV = qkv_dim(c),
+                QD = (int64_t)c.n_q_heads * c.head_dim;
+  auto expect = [&](int64_t r, int64_t cc) -> int {
+    B200Q_CHECK_ARG(rows == r && cols == cc, "weight %s has shape [%lld,%lld], expected [%lld,%lld]",
+                    name, (long long)rows, (long long)cols, (long long)r, (long long)cc);
+    return B200Q_OK;
+  };
+  int rc;
+  if (!strcmp(name, "embed")) {
+    if ((rc = expect(c.vocab, H))) return rc;
+    m->embed = p;
+    if (c.tie_embeddings) m->lm_head = p;
+    return B200Q_OK;
+  }
+  if (!strcmp(name, "final_norm")) {
+    if ((rc = expect(1, H))) return rc;
+    m->final_norm = p;
+    return B200Q_OK;
+  }
+  if (!strcmp(name, "lm_head")) {
+    if ((rc = expect(c.vocab, H))) return rc;
+    m->lm_head = p;
+    return B200Q_OK;
+  }
+  int li = -1;
+  char field[32] = {0};
+  if (sscanf(name, "layers.%d.%31s", &li, field) == 2 && li >= 0 && li < c.n_layers) {
+    b200q_layer& L = m->layers[li];
+    if (!strcmp(field, "input_norm")) { if ((rc = expect(1, H))) return rc; L.input_norm = p; return B200Q_OK; }
+    if (!strcmp(field, "post_norm")) { if ((rc = expect(1, H))) return rc; L.post_norm = p; return B200Q_OK; }
+    if (!strcmp(field, "qkv")) { if ((rc = expect(QKV, H))) return rc; L.qkv = p; return B200Q_OK; }
+    if (!strcmp(field, "o")) { if ((rc = expect(H, QD))) return rc; L.o = p; return B200Q_OK; }
+    if (!strcmp(field, "gate_up")) { if ((rc = expect(2 * I, H))) return rc; L.gate_up = p; return B200Q_OK; }
+    if (!strcmp(field, "down")) { if ((rc = expect(H, I))) return rc; L.down = p; return B200Q_OK; }
+  }
+  set_error("bind_weight: unknown weight name '%s'", name);
+  return B200Q_EINVAL;
+}
+
+int b200q_model_bind_kv(b200q_model_t m, void* p, int64_t num_blocks) {
+  B200Q_CHECK_ARG(m && p && num_blocks > 0, "bind_kv: bad argument");
+  B200Q_CHECK_ARG((reinterpret_cast<uintptr_t>(p) & 127) == 0, "kv cache must be 128-byte aligned");
+  m->kv = (uint8_t*)p;
+  m->num_blocks = num_blocks;
+  return B200Q_OK;
+}
+
+int b200q_model_bind_rope(b200q_model_t m, const void* p) {
+  B200Q_CHECK_ARG(m && p, "bind_rope: bad argument");
+  m->rope = p;
+  return B200Q_OK;
+}
+
+int b200q_model_bind_workspace(b200q_model_t m, void* p, int64_t bytes) {
+  B200Q_CHECK_ARG(m && p, "bind_workspace: bad argument");
+  const b200q_model_config& c = m->cfg;
+  const int64_t need = b200q_model_workspace_bytes(&c);
+  B200Q_CHECK_ARG(bytes >= need, "workspace too small: %lld < %lld", (long long)bytes,
+                  (long long)need);
+  B200Q_CHECK_ARG((reinterpret_cast<uintptr_t>(p) & 255) == 0, "workspace must be 256-byte aligned");
+  const int64_t T = c.max_tokens, S = c.max_seqs;
+  uint8_t* q = (uint8_t*)p;
+  auto take = [&](int64_t n) {
+    uint8_t* r = q;
+    q += align256(n);
+    return (bf16*)r;
+  };
+  m->ws = (uint8_t*)p;
+  m->ws_bytes = bytes;
+  m->x = take(T * c.hidden * 2);
+  m->residual = take(T * c.hidden * 2);
+  m->qkv = take(T * qkv_dim(c) * 2);
+  m->attn = take(T * (int64_t)c.n_q_heads * c.head_dim * 2);
+  m->gate_up = take(T * 2 * (int64_t)c.intermediate * 2);
+  m->act = take(T * (int64_t)c.intermediate * 2);
+  m->sel = take(S * (int64_t)c.hidden * 2);
+  m->logits = take(S * (int64_t)c.vocab * 2);
+  return B200Q_OK;
+}
+
+const void* b200q_model_logits_ptr(b200q_model_t m) { return m ? m->logits : nullptr; }
+
+int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
+  B200Q_CHECK_ARG(m && b, "forward: null argument");
+  const b200q_model_config& c = m->cfg;
+  if (!m->embed || !m->final_norm || !m->lm_head || !m->kv || !m->rope || !m->ws) {
+    set_error("forward: model not fully bound (embed/final_norm/lm_head/kv/rope/workspace)");
+    return B200Q_ESTATE;
+  }
+  for (int i = 0; i < c.n_layers; ++i) {
+    const b200q_layer& L = m->layers[i];
+    if (!L.input_norm || !L.qkv || !L.o || !L.post_norm || !L.gate_up || !L.down) {
+      set_error("forward: layer %d has unbound weights", i);
+      return B200Q_ESTATE;
+    }
+  }
+  const int T = b->T;
+  B200Q_CHECK_ARG(T >= 0 && T <= c.max_tokens, "forward: T=%d exceeds workspace (%d)", T,
+                  c.max_tokens);
+  B200Q_CHECK_ARG(b->n_dec >= 0 && b->n_dec <= T && b->n_sample >= 0 && b->n_sample <= c.max_seqs,
+                  "forward: bad batch n_dec=%d n_sample=%d", b->n_dec, b->n_sample);
+  if (T == 0) return B200Q_OK;
+
+  const int H = c.hidden, D = c.head_dim, NQ = c.n_q_heads, NKV = c.n_kv_heads, I = c.intermediate;
+  const int QKV = (int)qkv_dim(c), QD = NQ * D;
+  const int64_t kv_layer_bytes = m->num_blocks * 2 * (int64_t)NKV * c.block_size * D * 2;
+  int rc;
+#define B200Q_TRY(call) \
+  do {                  \
+    rc = (call);        \
+    if (rc) return rc;  \
+  } while (0)
+
+  B200Q_TRY(b200q_embed(b->token_ids, m->embed, m->residual, T, H, stream));
+  for (int li = 0; li < c.n_layers; ++li) {
+    const b200q_layer& L = m->layers[li];
+    uint8_t* kv_layer = m->kv + li * kv_layer_bytes;
+    if (li == 0)
+      B200Q_TRY(b200q_rmsnorm(m->residual, L.input_norm, m->x, T, H, c.rms_eps, stream));
+    else
+      B200Q_TRY(b200q_add_rmsnorm(m->x, m->residual, L.input_norm, T, H, c.rms_eps, stream));
+    B200Q_TRY(b200q_gemm_bf16(m->x, L.qkv, m->qkv, T, QKV, H, stream));
+    B200Q_TRY(b200q_rope_kvwrite(m->qkv, m->rope, b->positions, b->slot_mapping, kv_layer, T, NQ,
+                                 NKV, D, c.block_size, stream));
+    B200Q_TRY(b200q_decode_attn(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
+                                b->ctx_lens, b->n_dec, NQ, NKV, D, c.block_size, c.attn_scale,
+                                stream));
+    B200Q_TRY(b200q_prefill_attn(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
+                                 b->tiles, b->n_tiles, NQ, NKV, D, c.block_size, c.attn_scale,
+                                 stream));
+    B200Q_TRY(b200q_gemm_bf16(m->attn, L.o, m->x, T, H, QD, stream));
+    B200Q_TRY(b200q_add_rmsnorm(m->x, m->residual, L.post_norm, T, H, c.rms_eps, stream));
+    B200Q_TRY(b200q_gemm_bf16(m->x, L.gate_up, m->gate_up, T, 2 * I, H, stream));
+    B200Q_TRY(b200q_swiglu(m->gate_up, m->act, T, I, stream));
+    B200Q_TRY(b200q_gemm_bf16(m->act, L.down, m->x, T, H, I, stream));
+  }
+  if (b->n_sample > 0) {
+    // only the rows that sample need the final norm + LM head; add_rmsnorm runs on all rows
+    // because x/residual are per-row anyway and the gather wants the normalised value.
+    B200Q_TRY(b200q_add_rmsnorm(m->x, m->residual, m->final_norm, T, H, c.rms_eps, stream));
+    B200Q_TRY(b200q_gather_rows(m->x, b->sample_rows, m->sel, b->n_sample, H, stream));
+    B200Q_TRY(b200q_gemm_bf16(m->sel, m->lm_head, m->logits, b->n_sample, c.vocab, H, stream));
+    B200Q_TRY(b200q_argmax_bf16(m->logits, b->out_ids, b->n_sample, c.vocab, stream));
+  }
+#undef B200Q_TRY
+  return B200Q_OK;
+}
+
+}  // extern "C"
+
+// accessors for engine.cu
+namespace b200q {
+const b200q_model_config& model_cfg(b200q_model_t m) { return m->cfg; }
+int64_t model_num_blocks(b200q_model_t m) { return m->num_blocks; }
+}  // namespace b200q

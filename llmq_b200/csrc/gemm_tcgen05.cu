@@ -393,13 +393,24 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
   cudaStream_t st = as_stream(stream);
   int bn = g_gemm_force_bn;
   if (bn == 0) {
-    // largest N tile that still gives every SM a tile; wave count decides among candidates
+    // Every CTA walks ceil(tiles / SMs) tiles; measured on B200 (profiles/r1_microbench.md) a
+    // 128-wide tile costs ~0.85x and a 64-wide tile ~0.8x the time of a 256-wide one (the kernel
+    // is bound by per-SM operand ingest, not by the MMA), so pick the candidate with the least
+    // (tiles per CTA) x (relative tile time); ties go to the wider tile.
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
     const int sms = num_sms();
-    bn = 64;
-    if (N % 256 == 0 && (long long)m_tiles * (N / 256) >= sms) bn = 256;
-    else if (N % 128 == 0 && (long long)m_tiles * (N / 128) >= sms) bn = 128;
-    else if (N % 256 == 0 && (long long)m_tiles * (N / 64) < sms) bn = 64;
+    const int cand[3] = {256, 128, 64};
+    const double cost[3] = {1.0, 0.85, 0.8};
+    double best = 1e30;
+    for (int i = 0; i < 3; ++i) {
+      if (N % cand[i]) continue;
+      const long long tiles = (long long)m_tiles * (N / cand[i]);
+      const double t = (double)((tiles + sms - 1) / sms) * cost[i];
+      if (t < best - 1e-9) {
+        best = t;
+        bn = cand[i];
+      }
+    }
   }
   if (N % bn != 0) bn = (N % 128 == 0) ? 128 : 64;
   if (bn == 256) return launch_gemm<256>(A, W, C, M, N, K, st);

@@ -1,0 +1,313 @@
+"""Model-side host code of the b200 worker: config parsing, weight loading / synthesis, buffer
+allocation (PyTorch = allocator only) and binding into libb200q.
+
+Replaces what ``AsyncEngineArgs(model=...)`` + ``AsyncLLMEngine.from_engine_args`` do for the
+reference worker (ref:llmq/workers/vllm_worker.py:105-123): resolve the model, load bf16
+weights, size the paged KV pool from ``gpu_memory_utilization``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import math
+import os
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import torch
+
+from . import lib as L
+
+BLOCK_SIZE = 16
+
+
+@dataclass
+class ModelSpec:
+    hidden: int
+    n_layers: int
+    n_q_heads: int
+    n_kv_heads: int
+    head_dim: int
+    intermediate: int
+    vocab: int
+    rms_eps: float = 1e-5
+    rope_theta: float = 500000.0
+    rope_scaling: Optional[dict] = None
+    tie_embeddings: bool = False
+    max_position_embeddings: int = 8192
+    eos_token_id: Optional[int] = None
+    bos_token_id: Optional[int] = None
+    name: str = "llama"
+
+    @staticmethod
+    def from_hf_config(cfg: dict, name: str = "llama") -> "ModelSpec":
+        arch = (cfg.get("architectures") or ["LlamaForCausalLM"])[0]
+        if arch not in ("LlamaForCausalLM", "MistralForCausalLM"):
+            raise ValueError(f"unsupported architecture {arch!r}: the b200 worker implements Llama-style decoders")
+        hd = cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"]
+        rp = cfg.get("rope_parameters") if isinstance(cfg.get("rope_parameters"), dict) else None
+        theta = cfg.get("rope_theta") or (rp or {}).get("rope_theta") or 10000.0
+        scaling = cfg.get("rope_scaling")
+        if scaling is None and rp and rp.get("rope_type", "default") not in ("default", None):
+            scaling = rp
+        eos = cfg.get("eos_token_id")
+        if isinstance(eos, list):
+            eos = eos[0]
+        return ModelSpec(
+            hidden=cfg["hidden_size"], n_layers=cfg["num_hidden_layers"],
+            n_q_heads=cfg["num_attention_heads"],
+            n_kv_heads=cfg.get("num_key_value_heads", cfg["num_attention_heads"]),
+            head_dim=hd, intermediate=cfg["intermediate_size"], vocab=cfg["vocab_size"],
+            rms_eps=cfg.get("rms_norm_eps", 1e-5), rope_theta=float(theta), rope_scaling=scaling,
+            tie_embeddings=bool(cfg.get("tie_word_embeddings", False)),
+            max_position_embeddings=cfg.get("max_position_embeddings", 8192),
+            eos_token_id=eos, bos_token_id=cfg.get("bos_token_id"), name=name,
+        )
+
+    def to_hf_config(self) -> dict:
+        return {
+            "architectures": ["LlamaForCausalLM"], "model_type": "llama",
+            "hidden_size": self.hidden, "num_hidden_layers": self.n_layers,
+            "num_attention_heads": self.n_q_heads, "num_key_value_heads": self.n_kv_heads,
+            "head_dim": self.head_dim, "intermediate_size": self.intermediate,
+            "vocab_size": self.vocab, "rms_norm_eps": self.rms_eps, "rope_theta": self.rope_theta,
+            "rope_scaling": self.rope_scaling, "tie_word_embeddings": self.tie_embeddings,
+            "max_position_embeddings": self.max_position_embeddings, "hidden_act": "silu",
+            "attention_bias": False, "mlp_bias": False, "torch_dtype": "bfloat16",
+            "bos_token_id": self.bos_token_id, "eos_token_id": self.eos_token_id,
+        }
+
+    @property
+    def qkv_dim(self) -> int:
+        return (self.n_q_heads + 2 * self.n_kv_heads) * self.head_dim
+
+    def weight_bytes_per_step(self) -> int:
+        """bf16 bytes streamed per decode step: all layer matrices + LM head."""
+        per_layer = (self.qkv_dim * self.hidden + self.hidden * self.n_q_heads * self.head_dim
+                     + 3 * self.intermediate * self.hidden)
+        return 2 * (self.n_layers * per_layer + self.vocab * self.hidden)
+
+    def kv_bytes_per_token(self) -> int:
+        return 2 * self.n_layers * self.n_kv_heads * self.head_dim * 2
+
+
+# Appendix E of SURVEY.md
+LLAMA_3_8B = ModelSpec(hidden=4096, n_layers=32, n_q_heads=32, n_kv_heads=8, head_dim=128,
+                       intermediate=14336, vocab=128256, rms_eps=1e-5, rope_theta=500000.0,
+                       tie_embeddings=False, max_position_embeddings=8192, eos_token_id=128001,
+                       bos_token_id=128000, name="llama-3-8b")
+LLAMA_32_1B = ModelSpec(hidden=2048, n_layers=16, n_q_heads=32, n_kv_heads=8, head_dim=64,
+                        intermediate=8192, vocab=128256, rms_eps=1e-5, rope_theta=500000.0,
+                        rope_scaling={"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0,
+                                      "high_freq_factor": 4.0,
+                                      "original_max_position_embeddings": 8192},
+                        tie_embeddings=True, max_position_embeddings=131072, eos_token_id=128009,
+                        bos_token_id=128000, name="llama-3.2-1b")
+BUILTIN_SPECS = {"llama-3-8b": LLAMA_3_8B, "llama-3.2-1b": LLAMA_32_1B}
+
+
+def rope_table(max_pos: int, head_dim: int, theta: float, scaling: Optional[dict]) -> torch.Tensor:
+    """bf16 [max_pos, head_dim] = (cos | sin), computed in fp32 like HF's LlamaRotaryEmbedding
+    (incl. the llama3 frequency scaling) and cast to the activation dtype."""
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+    if scaling and scaling.get("rope_type", scaling.get("type")) == "llama3":
+        factor = scaling["factor"]
+        lo, hi = scaling["low_freq_factor"], scaling["high_freq_factor"]
+        orig = scaling["original_max_position_embeddings"]
+        wl = 2 * math.pi / inv
+        inv_l = torch.where(wl > orig / lo, inv / factor, inv)
+        smooth = (orig / wl - lo) / (hi - lo)
+        smoothed = (1 - smooth) * inv_l / factor + smooth * inv_l
+        mid = ~(wl < orig / hi) * ~(wl > orig / lo)
+        inv = torch.where(mid, smoothed, inv_l)
+    freqs = torch.outer(torch.arange(max_pos, dtype=torch.float32), inv)
+    return torch.cat([freqs.cos(), freqs.sin()], dim=-1).to(torch.bfloat16)
+
+
+def fuse_hf_weights(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Iterable[Tuple[str, torch.Tensor]]:
+    """HF checkpoint names -> engine names, with q/k/v and gate/up concatenated row-wise
+    (same fusion vLLM's QKVParallelLinear / MergedColumnParallelLinear perform)."""
+    yield "embed", sd["model.embed_tokens.weight"]
+    yield "final_norm", sd["model.norm.weight"].reshape(1, -1)
+    if not spec.tie_embeddings:
+        yield "lm_head", sd["lm_head.weight"]
+    for i in range(spec.n_layers):
+        p = f"model.layers.{i}."
+        yield f"layers.{i}.input_norm", sd[p + "input_layernorm.weight"].reshape(1, -1)
+        yield f"layers.{i}.post_norm", sd[p + "post_attention_layernorm.weight"].reshape(1, -1)
+        yield f"layers.{i}.qkv", torch.cat([sd[p + "self_attn.q_proj.weight"],
+                                            sd[p + "self_attn.k_proj.weight"],
+                                            sd[p + "self_attn.v_proj.weight"]], 0)
+        yield f"layers.{i}.o", sd[p + "self_attn.o_proj.weight"]
+        yield f"layers.{i}.gate_up", torch.cat([sd[p + "mlp.gate_proj.weight"],
+                                                sd[p + "mlp.up_proj.weight"]], 0)
+        yield f"layers.{i}.down", sd[p + "mlp.down_proj.weight"]
+
+
+def random_engine_weights(spec: ModelSpec, seed: int, device, std: float = 0.02):
+    """Random-init weights generated directly on the GPU in engine layout (benchmarks: there is
+    no checkpoint on disk and 16 GB of safetensors should not travel).  Normal(0, std), unit norms."""
+    g = torch.Generator(device=device).manual_seed(seed)
+
+    def mat(r, c):
+        return (torch.randn(r, c, generator=g, device=device, dtype=torch.float32) * std).to(torch.bfloat16)
+
+    ones = lambda: torch.ones(1, spec.hidden, dtype=torch.bfloat16, device=device)
+    yield "embed", mat(spec.vocab, spec.hidden)
+    yield "final_norm", ones()
+    if not spec.tie_embeddings:
+        yield "lm_head", mat(spec.vocab, spec.hidden)
+    for i in range(spec.n_layers):
+        yield f"layers.{i}.input_norm", ones()
+        yield f"layers.{i}.post_norm", ones()
+        yield f"layers.{i}.qkv", mat(spec.qkv_dim, spec.hidden)
+        yield f"layers.{i}.o", mat(spec.hidden, spec.n_q_heads * spec.head_dim)
+        yield f"layers.{i}.gate_up", mat(2 * spec.intermediate, spec.hidden)
+        yield f"layers.{i}.down", mat(spec.hidden, spec.intermediate)
+
+
+def load_hf_state_dict(model_dir: str) -> Dict[str, torch.Tensor]:
+    from safetensors.torch import load_file
+
+    files = sorted(f for f in os.listdir(model_dir) if f.endswith(".safetensors"))
+    if not files:
+        raise FileNotFoundError(f"no .safetensors files in {model_dir}")
+    sd: Dict[str, torch.Tensor] = {}
+    for f in files:
+        sd.update(load_file(os.path.join(model_dir, f)))
+    return sd
+
+
+def resolve_model(model_name: str) -> Tuple[ModelSpec, Optional[str]]:
+    """model_name is what the user passes to `llmq worker run <model> <queue>`: a local directory
+    with config.json (+ safetensors, tokenizer), or `random:<builtin>` for random-init
+    benchmarks (no network in this deployment, so hub ids must already be on disk)."""
+    if model_name.startswith("random:"):
+        key = model_name.split(":", 1)[1]
+        if key not in BUILTIN_SPECS:
+            raise ValueError(f"unknown builtin spec {key!r}; have {sorted(BUILTIN_SPECS)}")
+        return BUILTIN_SPECS[key], None
+    cfg_path = os.path.join(model_name, "config.json")
+    if not os.path.exists(cfg_path):
+        raise FileNotFoundError(f"{cfg_path} not found: pass a local model directory (offline deployment)")
+    with open(cfg_path) as f:
+        cfg = json.load(f)
+    return ModelSpec.from_hf_config(cfg, name=os.path.basename(os.path.normpath(model_name))), model_name
+
+
+class NativeModel:
+    """Owns the device buffers (weights, KV pool, RoPE table, workspace) and the b200q_model
+    handle they are bound to."""
+
+    def __init__(self, spec: ModelSpec, weights: Iterable[Tuple[str, torch.Tensor]], *,
+                 max_tokens: int = 4096, max_seqs: int = 256, max_model_len: int = 2048,
+                 num_blocks: Optional[int] = None, gpu_memory_utilization: float = 0.9,
+                 device: Optional[torch.device] = None):
+        L.require_device()
+        self.spec = spec
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.lib = L.load()
+        self.max_model_len = min(max_model_len, spec.max_position_embeddings)
+        self.cfg = L.ModelConfig(
+            hidden=spec.hidden, n_layers=spec.n_layers, n_q_heads=spec.n_q_heads,
+            n_kv_heads=spec.n_kv_heads, head_dim=spec.head_dim, intermediate=spec.intermediate,
+            vocab=spec.vocab, block_size=BLOCK_SIZE, max_tokens=max_tokens, max_seqs=max_seqs,
+            max_pos=self.max_model_len, tie_embeddings=int(spec.tie_embeddings),
+            rms_eps=spec.rms_eps, attn_scale=spec.head_dim ** -0.5)
+        h = C.c_void_p()
+        L.check(self.lib.b200q_model_create(C.byref(self.cfg), C.byref(h)))
+        self.handle = h
+        self._keep: List[torch.Tensor] = []
+        for name, t in weights:
+            t = t.to(device=self.device, dtype=torch.bfloat16).contiguous()
+            self._keep.append(t)
+            L.check(self.lib.b200q_model_bind_weight(h, name.encode(), t.data_ptr(), t.shape[0], t.shape[1]))
+        self.rope = rope_table(self.max_model_len, spec.head_dim, spec.rope_theta,
+                               spec.rope_scaling).to(self.device).contiguous()
+        L.check(self.lib.b200q_model_bind_rope(h, self.rope.data_ptr()))
+        ws_bytes = int(self.lib.b200q_model_workspace_bytes(C.byref(self.cfg)))
+        if ws_bytes <= 0:
+            raise L.B200QError(ws_bytes, "workspace sizing failed")
+        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        L.check(self.lib.b200q_model_bind_workspace(h, self.workspace.data_ptr(), ws_bytes))
+        block_bytes = spec.n_layers * 2 * spec.n_kv_heads * BLOCK_SIZE * spec.head_dim * 2
+        if num_blocks is None:
+            torch.cuda.synchronize(self.device)
+            free, total = torch.cuda.mem_get_info(self.device)
+            # same meaning as vLLM's gpu_memory_utilization: the worker may use this fraction of
+            # the device; what is left after weights + workspace becomes the paged KV pool
+            usable = int(total * gpu_memory_utilization) - (total - free)
+            num_blocks = max(usable // block_bytes, 0)
+        if num_blocks < (self.max_model_len + BLOCK_SIZE - 1) // BLOCK_SIZE:
+            raise MemoryError(f"KV pool of {num_blocks} blocks cannot hold one max_model_len sequence")
+        self.num_blocks = int(num_blocks)
+        self.kv = torch.zeros(spec.n_layers, self.num_blocks, 2, spec.n_kv_heads, BLOCK_SIZE,
+                              spec.head_dim, dtype=torch.bfloat16, device=self.device)
+        L.check(self.lib.b200q_model_bind_kv(h, self.kv.data_ptr(), self.num_blocks))
+        torch.cuda.synchronize(self.device)
+
+    def logits_view(self, n: int) -> torch.Tensor:
+        """bf16 [n, vocab] view of the logits written by the last forward (tests only)."""
+        ptr = self.lib.b200q_model_logits_ptr(self.handle)
+        off = ptr - self.workspace.data_ptr()
+        return self.workspace[off: off + n * self.spec.vocab * 2].view(torch.bfloat16).view(n, self.spec.vocab)
+
+    def close(self):
+        if self.handle:
+            self.lib.b200q_model_destroy(self.handle)
+            self.handle = None
+
+
+class Engine:
+    """Python face of b200q_engine: add requests, run steps, get (req_id, token, flags) events."""
+
+    def __init__(self, model: NativeModel, *, max_num_seqs: int, max_num_batched_tokens: int,
+                 max_model_len: Optional[int] = None, eos_token_id: Optional[int] = None):
+        import numpy as np
+
+        self.model = model
+        self.lib = model.lib
+        self.np = np
+        ecfg = L.EngineConfig(
+            max_num_seqs=max_num_seqs, max_num_batched_tokens=max_num_batched_tokens,
+            max_model_len=max_model_len or model.max_model_len,
+            eos_token_id=-1 if eos_token_id is None else int(eos_token_id))
+        h = C.c_void_p()
+        L.check(self.lib.b200q_engine_create(model.handle, C.byref(ecfg), C.byref(h)))
+        self.handle = h
+        self.cap = max_num_seqs
+        self._ids = np.zeros(self.cap, dtype=np.int64)
+        self._tok = np.zeros(self.cap, dtype=np.int32)
+        self._flg = np.zeros(self.cap, dtype=np.int32)
+
+    def add_request(self, req_id: int, prompt_ids, max_new_tokens: int, ignore_eos: bool = False):
+        arr = self.np.ascontiguousarray(prompt_ids, dtype=self.np.int32)
+        rc = self.lib.b200q_engine_add_request(self.handle, int(req_id), arr.ctypes.data, arr.size,
+                                               int(max_new_tokens), int(ignore_eos))
+        if rc == -1:  # B200Q_EINVAL: an un-servable job, the worker drops it (ValueError)
+            raise ValueError(self.lib.b200q_last_error().decode())
+        L.check(rc)
+
+    def abort(self, req_id: int):
+        L.check(self.lib.b200q_engine_abort(self.handle, int(req_id)))
+
+    def has_work(self) -> bool:
+        return bool(self.lib.b200q_engine_has_work(self.handle))
+
+    def step(self):
+        """returns three numpy arrays (views, valid until the next step): ids, tokens, flags"""
+        n = C.c_int32(0)
+        L.check(self.lib.b200q_engine_step(self.handle, self._ids.ctypes.data, self._tok.ctypes.data,
+                                           self._flg.ctypes.data, self.cap, C.byref(n)))
+        k = n.value
+        return self._ids[:k], self._tok[:k], self._flg[:k]
+
+    def stats(self) -> L.EngineStats:
+        s = L.EngineStats()
+        L.check(self.lib.b200q_engine_get_stats(self.handle, C.byref(s)))
+        return s
+
+    def close(self):
+        if self.handle:
+            self.lib.b200q_engine_destroy(self.handle)
+            self.handle = None

@@ -1,0 +1,194 @@
+"""GPU parity of the whole forward step and of the continuous-batching engine against the CPU
+oracle (oracle/model.py), on small seeded Llama-shaped models, plus the size-independent
+properties (batch invariance, determinism, preemption transparency) used at full size."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+from oracle.model import LlamaDims, LlamaOracle, random_llama_weights
+
+pytestmark = pytest.mark.gpu
+
+TINY = {
+    "d64": LlamaDims(hidden=256, n_layers=2, n_q_heads=8, n_kv_heads=2, head_dim=64,
+                     intermediate=512, vocab=1024, max_pos=512),
+    "d128": LlamaDims(hidden=512, n_layers=3, n_q_heads=8, n_kv_heads=2, head_dim=128,
+                      intermediate=1024, vocab=2048, max_pos=512),
+    "d64_tied_llama3rope": LlamaDims(hidden=256, n_layers=2, n_q_heads=8, n_kv_heads=2, head_dim=64,
+                                     intermediate=512, vocab=1024, max_pos=512, tie_embeddings=True,
+                                     rope_scaling={"rope_type": "llama3", "factor": 32.0,
+                                                   "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                                                   "original_max_position_embeddings": 64}),
+}
+
+
+def build(dims: LlamaDims, seed=1, **kw):
+    from llmq_b200.model import ModelSpec, NativeModel, fuse_hf_weights
+    w = random_llama_weights(dims, seed=seed)
+    spec = ModelSpec(hidden=dims.hidden, n_layers=dims.n_layers, n_q_heads=dims.n_q_heads,
+                     n_kv_heads=dims.n_kv_heads, head_dim=dims.head_dim,
+                     intermediate=dims.intermediate, vocab=dims.vocab, rms_eps=dims.rms_eps,
+                     rope_theta=dims.rope_theta, rope_scaling=dims.rope_scaling,
+                     tie_embeddings=dims.tie_embeddings, max_position_embeddings=dims.max_pos)
+    kw.setdefault("max_tokens", 512)
+    kw.setdefault("max_seqs", 64)
+    kw.setdefault("max_model_len", dims.max_pos)
+    kw.setdefault("num_blocks", 256)
+    model = NativeModel(spec, fuse_hf_weights(spec, w), **kw)
+    return model, LlamaOracle(dims, w, "bf16"), w
+
+
+def prompts(vocab, lens, seed=5):
+    g = np.random.default_rng(seed)
+    return [g.integers(3, vocab, size=n).tolist() for n in lens]
+
+
+@pytest.mark.parametrize("name", list(TINY))
+def test_rope_table_matches_oracle(cuda, name):
+    from llmq_b200.model import rope_table
+    d = TINY[name]
+    a = rope_table(d.max_pos, d.head_dim, d.rope_theta, d.rope_scaling).float()
+    assert torch.equal(a, O.rope_table(d.max_pos, d.head_dim, d.rope_theta, d.rope_scaling))
+
+
+@pytest.mark.parametrize("name", list(TINY))
+def test_forward_logits_teacher_forced(cuda, name):
+    """one prefill of n tokens with every row sampled: logits for all positions vs the oracle"""
+    from llmq_b200 import lib as L
+    dims = TINY[name]
+    model, oracle, _ = build(dims)
+    n = 45
+    ids = torch.tensor(prompts(dims.vocab, [n])[0], dtype=torch.int32)
+    BS = 16
+    nb = (n + BS - 1) // BS
+    blocks = [7, 3, 11][:nb]
+    meta = {
+        "tok": ids, "pos": torch.arange(n, dtype=torch.int32),
+        "slot": torch.tensor([blocks[p // BS] * BS + p % BS for p in range(n)], dtype=torch.int32),
+        "bt": torch.tensor([blocks + [0] * (8 - nb)], dtype=torch.int32),
+        "ctx": torch.zeros(1, dtype=torch.int32),
+        "tiles": torch.tensor([[0, j, min(16, n - j), j] for j in range(0, n, 16)], dtype=torch.int32),
+        "rows": torch.arange(n, dtype=torch.int32),
+    }
+    dev = {k: v.to(cuda).contiguous() for k, v in meta.items()}
+    out = torch.zeros(n, dtype=torch.int32, device=cuda)
+    b = L.Batch(T=n, n_dec=0, n_tiles=dev["tiles"].shape[0], n_sample=n, bt_stride=8,
+                token_ids=dev["tok"].data_ptr(), positions=dev["pos"].data_ptr(),
+                slot_mapping=dev["slot"].data_ptr(), block_table=dev["bt"].data_ptr(),
+                ctx_lens=dev["ctx"].data_ptr(), tiles=dev["tiles"].data_ptr(),
+                sample_rows=dev["rows"].data_ptr(), out_ids=out.data_ptr())
+    L.check(model.lib.b200q_model_forward(model.handle, C.byref(b), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = model.logits_view(n).float().cpu()
+    ref, _ = oracle.forward(ids.long(), torch.arange(n))
+    diff = (got - ref).abs()
+    # stated tolerance: logits within 0.06 absolute (bf16 activations, ~3 layers), mean < 0.01
+    assert diff.max().item() < 0.06 and diff.mean().item() < 0.01, (diff.max().item(), diff.mean().item())
+    top2 = ref.topk(2, -1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 0.12
+    assert np.array_equal(out.cpu().numpy()[safe.numpy()], O.argmax_first(ref)[safe.numpy()])
+    assert np.array_equal(out.cpu().numpy(), O.argmax_first(got)), "argmax kernel vs its own logits"
+    model.close()
+
+
+def run_engine(model, reqs, max_new, **ekw):
+    from llmq_b200.model import Engine
+    ekw.setdefault("max_num_seqs", 16)
+    ekw.setdefault("max_num_batched_tokens", 256)
+    eng = Engine(model, eos_token_id=None, **ekw)
+    for i, p in enumerate(reqs):
+        eng.add_request(i, p, max_new, ignore_eos=True)
+    outs = {i: [] for i in range(len(reqs))}
+    done = set()
+    guard = 0
+    while eng.has_work():
+        ids, toks, flags = eng.step()
+        for i, t, f in zip(ids.tolist(), toks.tolist(), flags.tolist()):
+            outs[i].append(t)
+            if f:
+                done.add(i)
+        guard += 1
+        assert guard < 10000
+    st = eng.stats()
+    eng.close()
+    assert done == set(range(len(reqs)))
+    return outs, st
+
+
+def check_against_oracle(oracle, reqs, outs, max_new, margin_tol=0.12):
+    exact = 0
+    for i, p in enumerate(reqs):
+        ref, lg = oracle.greedy(p, max_new, return_logits=True)
+        got = outs[i]
+        assert len(got) == max_new
+        if got == ref:
+            exact += 1
+            continue
+        k = next(j for j in range(max_new) if got[j] != ref[j])
+        top2 = lg[k].topk(2).values
+        margin = (top2[0] - top2[1]).item()
+        assert margin < margin_tol, (
+            f"request {i}: first divergence at token {k} (got {got[k]}, oracle {ref[k]}) with a "
+            f"top-2 logit margin of {margin:.4f} >= tolerance {margin_tol}")
+        assert got[k] in lg[k].topk(4).indices.tolist()
+    return exact
+
+
+@pytest.mark.parametrize("name", list(TINY))
+def test_engine_greedy_matches_oracle(cuda, name):
+    dims = TINY[name]
+    model, oracle, _ = build(dims)
+    reqs = prompts(dims.vocab, [1, 5, 16, 17, 40, 130, 64, 33, 2, 100])
+    outs, st = run_engine(model, reqs, max_new=12)
+    exact = check_against_oracle(oracle, reqs, outs, 12)
+    assert exact >= len(reqs) - 3, f"only {exact}/{len(reqs)} requests matched the oracle exactly"
+    assert st.tokens_decoded > 0 and st.tokens_prefilled == sum(len(r) for r in reqs)
+    model.close()
+
+
+def test_engine_batch_invariance_chunking_and_preemption(cuda):
+    """size-independent properties: the tokens of a request do not depend on what else is in the
+    batch, on how its prompt is chunked, or on being preempted and recomputed."""
+    dims = TINY["d128"]
+    model, oracle, _ = build(dims, num_blocks=40)
+    reqs = prompts(dims.vocab, [70, 3, 129, 31, 16, 200, 9, 48], seed=9)
+    alone = {}
+    for i, p in enumerate(reqs):
+        o, _ = run_engine(model, [p], max_new=10)
+        alone[i] = o[0]
+    together, st1 = run_engine(model, reqs, max_new=10)
+    # tiny budget: chunked prefill (budget 24 < prompt lengths); tiny pool (40 blocks of 16 tokens
+    # < sum of all sequences = 506+80 tokens ~ 41 blocks) forces preemption + recompute
+    chunked, st2 = run_engine(model, reqs, max_new=10, max_num_batched_tokens=24, max_num_seqs=8)
+    twice, _ = run_engine(model, reqs, max_new=10)
+    for i in range(len(reqs)):
+        assert together[i] == twice[i], "non-deterministic across identical runs"
+    # decode vs prefill attention paths round differently; allow divergence only at near-ties
+    check_against_oracle(oracle, reqs, together, 10)
+    check_against_oracle(oracle, reqs, chunked, 10)
+    check_against_oracle(oracle, reqs, alone, 10)
+    n_same = sum(together[i] == alone[i] for i in range(len(reqs)))
+    assert n_same >= len(reqs) - 1, f"batch invariance broken for {len(reqs) - n_same} requests"
+    model.close()
+
+
+def test_engine_rejects_unservable_requests(cuda):
+    from llmq_b200.model import Engine
+    dims = TINY["d64"]
+    model, _, _ = build(dims, max_model_len=64)
+    eng = Engine(model, max_num_seqs=4, max_num_batched_tokens=64, eos_token_id=2)
+    with pytest.raises(ValueError):
+        eng.add_request(1, list(range(3, 3 + 64)), 4)  # prompt fills the whole context window
+    with pytest.raises(ValueError):
+        eng.add_request(2, [5, dims.vocab + 1], 4)  # token id out of range
+    eng.add_request(3, [5, 6, 7], 1000)  # clipped to the context window, finishes by length
+    n = 0
+    while eng.has_work():
+        ids, toks, flags = eng.step()
+        n += len(ids)
+    assert 1 <= n <= 61
+    eng.close()
+    model.close()

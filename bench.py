@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the b200 worker's hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # native arm
+  python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
+
+Workload (BASELINE.json `metric`): Llama-3-8B, random-init bf16, 128 prompt tokens in / 128
+generated tokens out, queue-sharded data parallel — one worker process per GPU, job i of the
+canonical seeded job stream goes to rank i % N, no data-path collective.
+
+A *step* is one batch of `--jobs` jobs per GPU pushed through the continuous-batching engine to
+completion (prefill + 128 greedy decode tokens each).
+  value : output tokens/s with the prompts already tokenised and queued inside the engine
+          (weights, KV pool, workspace resident in HBM) — device-side, max over ranks.
+  e2e   : the same metric through the worker-facing call (`GenerationService.submit`, what
+          `B200Worker._process_job` awaits): host text prompts -> tokenise -> engine thread ->
+          per-step H2D metadata / D2H sampled ids -> detokenise -> host text.
+  roofline : live CUDA-event timing of every kernel launch in the timed region (events recorded
+          on the engine's stream by libb200q), GEMM = dominant kernel (tensor-bound), plus the
+          decode-attention HBM fraction.
+  cpu_baseline / --impl reference : the CPU oracle (oracle/model.py, a torch-CPU restatement
+          of the vLLM/HF Llama forward; vLLM-CPU is not installable here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import asyncio
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "output_tokens_per_sec"
+UNIT = "tokens/s"
+
+
+def ensure_llmq_importable():
+    """the reference package (pip --target baseline/_ref) + the aio_pika/semhash
+    stand-ins this image lacks (tests/shims) — needed to instantiate the real BaseWorker slot"""
+    try:
+        import aio_pika  # noqa: F401
+    except ImportError:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "shims"))
+    try:
+        import llmq.workers.base  # noqa: F401
+    except ImportError:
+        for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+            if os.path.isdir(os.path.join(p, "llmq")):
+                sys.path.insert(0, p)
+                break
+        import llmq.workers.base  # noqa: F401
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "bf16_tflops_burst": d["bf16_tflops"], "source": "MEASURED_PEAKS.json (sustained bf16, copy HBM)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (the oracle port), also used for the cpu_baseline key of the native arm
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(model_key: str, prompt_tokens: int, out_tokens: int, budget_s: float):
+    """One bounded sample of the workload on the host cores: a real 128-token prefill plus as many
+    greedy decode steps as fit in `budget_s`, extrapolated to a full 128-out job.  To bound host
+    RAM and init time the 32 decoder layers share ONE set of random layer weights (same shapes,
+    same FLOPs and bytes per layer; the outputs are not used for parity)."""
+    import torch
+
+    from llmq_b200.model import BUILTIN_SPECS
+    from oracle.model import LlamaDims, LlamaOracle
+
+    spec = BUILTIN_SPECS[model_key]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dims = LlamaDims(hidden=spec.hidden, n_layers=spec.n_layers, n_q_heads=spec.n_q_heads,
+                     n_kv_heads=spec.n_kv_heads, head_dim=spec.head_dim, intermediate=spec.intermediate,
+                     vocab=spec.vocab, rms_eps=spec.rms_eps, rope_theta=spec.rope_theta,
+                     rope_scaling=spec.rope_scaling, tie_embeddings=spec.tie_embeddings, max_pos=512)
+    g = torch.Generator().manual_seed(7)
+    mat = lambda r, c: torch.randn(r, c, generator=g) * 0.02
+    qd, kd = dims.n_q_heads * dims.head_dim, dims.n_kv_heads * dims.head_dim
+    layer = {"input_layernorm.weight": torch.ones(dims.hidden), "post_attention_layernorm.weight": torch.ones(dims.hidden),
+             "self_attn.q_proj.weight": mat(qd, dims.hidden), "self_attn.k_proj.weight": mat(kd, dims.hidden),
+             "self_attn.v_proj.weight": mat(kd, dims.hidden), "self_attn.o_proj.weight": mat(dims.hidden, qd),
+             "mlp.gate_proj.weight": mat(dims.intermediate, dims.hidden), "mlp.up_proj.weight": mat(dims.intermediate, dims.hidden),
+             "mlp.down_proj.weight": mat(dims.hidden, dims.intermediate)}
+    w = {"model.embed_tokens.weight": mat(dims.vocab, dims.hidden), "model.norm.weight": torch.ones(dims.hidden)}
+    if not dims.tie_embeddings:
+        w["lm_head.weight"] = w["model.embed_tokens.weight"]  # same shape; shares storage
+    for i in range(dims.n_layers):
+        for k, v in layer.items():
+            w[f"model.layers.{i}.{k}"] = v
+    oracle = LlamaOracle.__new__(LlamaOracle)  # skip the per-tensor copies of __init__
+    from oracle import ops as O
+    oracle.d, oracle.mode, oracle.w = dims, "fp32", w
+    oracle.table = O.rope_table(512, dims.head_dim, dims.rope_theta, dims.rope_scaling, "fp32")
+    oracle.scale = dims.head_dim ** -0.5
+    ids = torch.randint(0, dims.vocab, (prompt_tokens,), generator=g)
+
+    def sample():
+        t0 = time.perf_counter()
+        logits, kv = oracle.forward(ids, torch.arange(prompt_tokens), None, all_logits=False)
+        t_prefill = time.perf_counter() - t0
+        n_dec, t_dec = 0, 0.0
+        tok = int(logits[-1].argmax())
+        while n_dec < out_tokens - 1 and (t_prefill + t_dec) < budget_s:
+            t1 = time.perf_counter()
+            logits, kv = oracle.forward(torch.tensor([tok]), torch.tensor([prompt_tokens + n_dec]), kv, all_logits=False)
+            tok = int(logits[-1].argmax())
+            t_dec += time.perf_counter() - t1
+            n_dec += 1
+        per_dec = t_dec / max(n_dec, 1)
+        t_job = t_prefill + (out_tokens - 1) * per_dec
+        return {"t_prefill_s": t_prefill, "decode_steps_timed": n_dec, "s_per_decode_token": per_dec,
+                "s_per_job_extrapolated": t_job, "tokens_per_s": out_tokens / t_job, "jobs_per_s": 1.0 / t_job}
+
+    return sample, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample, cores = cpu_reference_sample(args.model, args.prompt_tokens, args.out_tokens, args.cpu_budget_s)
+    if args.warmup > 0:
+        sample()  # one warm-up pass faults in the weights; more would only burn host time
+    t0 = time.perf_counter()
+    res = [sample() for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    tps = statistics.median(r["tokens_per_s"] for r in res)
+    desc = (f"1 job per step on {cores} host threads (torch-CPU fp32 oracle, one batch row): real {args.prompt_tokens}-token prefill + "
+            f"{res[0]['decode_steps_timed']} timed greedy decode steps, extrapolated to {args.out_tokens} output tokens; "
+            "32 layers share one random layer's weights")
+    line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cpu)", "data": "synthetic",
+            "config": workload_config(args, per_gpu_jobs=1),
+            "jobs_per_sec": statistics.median(r["jobs_per_s"] for r in res),
+            "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, per_gpu_jobs):
+    return {"workload": f"{args.model} random-init bf16, {args.prompt_tokens}-in/{args.out_tokens}-out greedy, "
+                        f"{per_gpu_jobs} jobs per step per GPU, queue-sharded (job i -> rank i % N)",
+            "max_num_seqs": args.max_num_seqs, "max_num_batched_tokens": args.max_num_batched_tokens,
+            "kv_block_size": 16, "l2": "working set per step (weights 15 GB + KV) >> 126 MB L2, no flush needed",
+            "parallelism": f"dp{args.gpus} (independent replicas, no collective)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import numpy as np
+    import torch
+
+    from llmq_b200 import lib as L
+    from llmq_b200.fixtures import make_jobs
+    from llmq_b200.service import GenerationService, build_service
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    torch.cuda.set_device(local)
+    L.require_device()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks = load_peaks()
+    svc: GenerationService = build_service(
+        f"random:{args.model}", max_num_seqs=args.max_num_seqs, max_model_len=args.max_model_len,
+        gpu_memory_utilization=0.9, max_num_batched_tokens=args.max_num_batched_tokens, seed=1234 + rank)
+    eng, model, tok = svc.engine, svc.engine.model, svc.tokenizer
+    spec = model.spec
+    n_steps_total = args.warmup + args.steps
+    J = args.jobs
+    # canonical seeded job stream; this rank's shard (queue-sharding by job index)
+    total_jobs = 2 * n_steps_total * J * world
+    jobs = make_jobs(total_jobs, spec.vocab, args.prompt_tokens - 1, start=rank, stride=world)
+    jobs_a, jobs_b = jobs[: n_steps_total * J], jobs[n_steps_total * J:]
+    ext_stream = torch.cuda.ExternalStream(eng.stream_ptr)
+
+    # ---- arm A: engine-direct (prompts tokenised and queued before the clock starts) ----
+    def step_direct(batch_jobs):
+        ids = [tok(j["prompt"], add_special_tokens=True).input_ids for j in batch_jobs]
+        for i, p in enumerate(ids):
+            eng.add_request(i, p, args.out_tokens, ignore_eos=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext_stream)
+        n_tok = 0
+        while eng.has_work():
+            _, toks, _ = eng.step()
+            n_tok += len(toks)
+        e1.record(ext_stream)
+        barrier()
+        return e0.elapsed_time(e1) / 1e3, n_tok
+
+    # ---- arm B: end to end through the worker-facing service call (host text in / text out) ----
+    os.environ["VLLM_MAX_TOKENS"] = str(args.out_tokens)
+    os.environ.setdefault("LLMQ_LOG_LEVEL", "WARNING")
+    ensure_llmq_importable()
+    from llmq.core.models import Job
+
+    from llmq_b200.worker import B200Worker
+
+    worker = B200Worker(f"random:{args.model}", "bench-queue", tensor_parallel_size=1)
+    worker.service = svc  # the engine built above (one model per process)
+
+    async def _e2e(batch_jobs):
+        # the reference-facing call: BaseWorker._process_message awaits exactly this coroutine
+        async def one(j):
+            text = await worker._process_job(Job(**j))
+            return len(text.split())
+
+        return await asyncio.gather(*[one(j) for j in batch_jobs])
+
+    def step_e2e(batch_jobs):
+        barrier()
+        t0 = time.perf_counter()
+        res = asyncio.run(_e2e(batch_jobs))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        return dt, sum(res)  # generated tokens: one word per ordinary token of the synthetic vocab
+
+    def reduce_max(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- arm A ----------------
+    for s in range(args.warmup):
+        step_direct(jobs_a[s * J:(s + 1) * J])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    model.set_profiling(True)
+    model.collect_profile(reset=True)
+    st0 = eng.stats()
+    launches0 = L.launch_count()
+    times_a, toks_a = [], 0
+    barrier()
+    for s in range(args.warmup, n_steps_total):
+        dt, n = step_direct(jobs_a[s * J:(s + 1) * J])
+        times_a.append(reduce_max(dt))
+        toks_a += n
+    barrier()
+    prof = model.collect_profile(reset=True)
+    model.set_profiling(False)
+    launches = L.launch_count() - launches0
+    st1 = eng.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    total_a = sum(times_a)
+    toks_all = reduce_sum(toks_a)
+    value = toks_all / total_a
+    jobs_per_s = world * J * args.steps / total_a
+
+    # ---------------- arm B (e2e) ----------------
+    svc.start()
+    for s in range(args.warmup):
+        step_e2e(jobs_b[s * J:(s + 1) * J])
+    sb0 = eng.stats()
+    times_b, toks_b = [], 0
+    for s in range(args.warmup, n_steps_total):
+        dt, n = step_e2e(jobs_b[s * J:(s + 1) * J])
+        times_b.append(reduce_max(dt))
+        toks_b += n
+    sb1 = eng.stats()
+    svc.stop()
+    e2e_value = reduce_sum(toks_b) / sum(times_b)
+
+    # ---------------- rooflines ----------------
+    g = prof["gemm"]
+    gemm_tflops = g["work"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
+    d = prof["decode_attn"]
+    dec_gbs = d["work"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
+    dev_ms = sum(v["ms"] for v in prof.values())
+    shares = {k: round(v["ms"] / dev_ms, 4) if dev_ms else 0 for k, v in prof.items()}
+    roofline = {"bound": "tensor", "kernel": "b200q::gemm_bf16_kernel<BN> (tcgen05)", "achieved": round(gemm_tflops, 1),
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": round(gemm_tflops / peaks["bf16_tflops"], 4),
+                "traffic": None, "peak_source": peaks["source"],
+                "launch_avg_ms": round(g["ms"] / max(g["launches"], 1), 5), "launches": g["launches"],
+                "share_of_device_time": shares}
+    roofline_dec = {"bound": "hbm", "kernel": "b200q::decode_attn_kernel<128,16>", "achieved": round(dec_gbs, 1),
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(dec_gbs / peaks["hbm_gbs"], 4),
+                    "launch_avg_ms": round(d["ms"] / max(d["launches"], 1), 5), "launches": d["launches"]}
+    # whole-step decode HBM roofline fraction: algorithmic bytes per output token
+    steps_a = st1.steps - st0.steps
+    dec_tokens = st1.tokens_decoded - st0.tokens_decoded
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            sample, cores = cpu_reference_sample(args.model, args.prompt_tokens, args.out_tokens, args.cpu_budget_s)
+            r = sample()
+            cpu = {"value": r["tokens_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+                   "jobs_per_sec": r["jobs_per_s"],
+                   "sample": f"1 job: real {args.prompt_tokens}-token prefill ({r['t_prefill_s']:.2f} s) + {r['decode_steps_timed']} timed decode "
+                             f"steps ({r['s_per_decode_token'] * 1e3:.1f} ms/token) extrapolated to {args.out_tokens} out tokens; torch-CPU fp32 "
+                             "oracle, all host threads, 32 layers share one random layer's weights"}
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(total_a / args.steps * 1e3, 2), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(args, J), "jobs_per_sec": round(jobs_per_s, 2),
+                "e2e": {"value": round(e2e_value, 1), "unit": UNIT,
+                        "jobs_per_sec": round(world * J * args.steps / sum(times_b), 2),
+                        "h2d_bytes_per_step": int((sb1.h2d_bytes - sb0.h2d_bytes) / args.steps),
+                        "d2h_bytes_per_step": int((sb1.d2h_bytes - sb0.d2h_bytes) / args.steps),
+                        "note": "B200Worker._process_job(Job) on host text: format prompt -> tokenise -> engine thread (H2D metadata / D2H ids every step) -> detokenised text"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "roofline_decode_attn": roofline_dec,
+                "engine": {"engine_steps_per_bench_step": steps_a / args.steps, "decode_tokens": int(dec_tokens),
+                           "preemptions": int(st1.preemptions - st0.preemptions), "kv_blocks": int(st1.total_blocks),
+                           "device_ms_profiled": round(dev_ms, 1), "wall_ms_timed": round(total_a * 1e3, 1)},
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    model.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--model", default="llama-3-8b")
+    ap.add_argument("--jobs", type=int, default=1024, help="jobs per step per GPU")
+    ap.add_argument("--prompt-tokens", type=int, default=128)
+    ap.add_argument("--out-tokens", type=int, default=128)
+    ap.add_argument("--max-num-seqs", type=int, default=1024)
+    ap.add_argument("--max-num-batched-tokens", type=int, default=8192)
+    ap.add_argument("--max-model-len", type=int, default=512)
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,9 @@ typedef struct b200q_batch {
   const int32_t* tiles;         /* [n_tiles][4]                                                 */
   const int32_t* sample_rows;   /* [n_sample] batch rows whose hidden state feeds the LM head   */
   int32_t* out_ids;             /* [n_sample] sampled token ids                                 */
+  /* host-side bookkeeping for the profiler (algorithmic work of this step's attention) */
+  int64_t sum_ctx_dec;          /* sum of ctx_lens over the decode sequences                    */
+  int64_t prefill_flops_per_layer; /* causal QK^T + PV flops of the prefill tiles, one layer     */
 } b200q_batch;
 
 int b200q_model_create(const b200q_model_config* cfg, b200q_model_t* out);
@@ -166,6 +169,20 @@ int b200q_model_bind_workspace(b200q_model_t m, void* dev_ptr, int64_t bytes);
 int b200q_model_forward(b200q_model_t m, const b200q_batch* batch, void* stream);
 /* debugging / parity: copy the bf16 logits of the last forward ([n_sample, V]) location */
 const void* b200q_model_logits_ptr(b200q_model_t m);
+/* per-category device timing: CUDA events recorded on the forward's stream around every launch
+ * (bench.py's live roofline numbers).  work = algorithmic flops (GEMM, prefill attention) or
+ * bytes (decode attention, elementwise) summed over the timed launches. */
+#define B200Q_PROF_GEMM 0
+#define B200Q_PROF_DECODE_ATTN 1
+#define B200Q_PROF_PREFILL_ATTN 2
+#define B200Q_PROF_ELEMENTWISE 3
+typedef struct b200q_profile {
+  double ms[4];
+  double work[4];
+  int64_t launches[4];
+} b200q_profile;
+int b200q_model_set_profiling(b200q_model_t m, int on);
+int b200q_model_profile_collect(b200q_model_t m, b200q_profile* out, int reset);
 /* number of kernels launched by this library since load (gpu_launches evidence) */
 int64_t b200q_launch_count(void);
 
@@ -201,6 +218,8 @@ typedef struct b200q_engine_stats {
   int32_t total_blocks;
   int32_t last_step_tokens;
   int32_t last_step_seqs;
+  int64_t h2d_bytes;   /* per-step metadata copies (token ids, block tables, ...) */
+  int64_t d2h_bytes;   /* sampled token ids read back                              */
 } b200q_engine_stats;
 
 int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b200q_engine_t* out);
@@ -217,6 +236,8 @@ int b200q_engine_has_work(b200q_engine_t e);
 int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_tokens,
                       int32_t* out_flags, int32_t cap, int32_t* n_out);
 int b200q_engine_get_stats(b200q_engine_t e, b200q_engine_stats* out);
+/* the engine's CUDA stream (cudaStream_t) so callers can record their own events on it */
+void* b200q_engine_stream(b200q_engine_t e);
 
 #ifdef __cplusplus
 }

@@ -187,6 +187,8 @@ int b200q_engine_abort(b200q_engine_t e, int64_t req_id) {
   return B200Q_OK;
 }
 
+void* b200q_engine_stream(b200q_engine_t e) { return e ? (void*)e->stream : nullptr; }
+
 int b200q_engine_has_work(b200q_engine_t e) {
   return e && (!e->waiting.empty() || !e->running.empty()) ? 1 : 0;
 }
@@ -350,6 +352,19 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
   b.tiles = e->d_meta + (tiles - e->h_meta);
   b.block_table = e->d_meta + (btab - e->h_meta);
   b.out_ids = e->d_out;
+  b.sum_ctx_dec = 0;
+  b.prefill_flops_per_layer = 0;
+  for (Request* r : sched) {
+    if (r->n_sched == 1) {
+      b.sum_ctx_dec += r->n_computed + 1;
+    } else {
+      // causal: query j of the chunk sees n_computed + j + 1 keys; QK^T and PV, 2 flops per MAC
+      const double q = r->n_sched, c0 = r->n_computed;
+      const double pairs = q * c0 + q * (q + 1) / 2;
+      b.prefill_flops_per_layer +=
+          (int64_t)(4.0 * pairs * e->mcfg.n_q_heads * e->mcfg.head_dim);
+    }
+  }
   int rc = b200q_model_forward(e->model, &b, e->stream);
   if (rc) return rc;
   if (n_sample > 0) {
@@ -366,6 +381,8 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
   }
 
   // ---- 4. update from output ----
+  e->stats.h2d_bytes += used * 4;
+  e->stats.d2h_bytes += (int64_t)n_sample * 4;
   e->stats.steps++;
   e->stats.last_step_tokens = T;
   e->stats.last_step_seqs = n_rows;

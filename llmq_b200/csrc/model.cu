@@ -34,6 +34,21 @@ struct b200q_model {
   int64_t ws_bytes = 0;
   bf16 *x = nullptr, *residual = nullptr, *qkv = nullptr, *attn = nullptr, *gate_up = nullptr,
        *act = nullptr, *sel = nullptr, *logits = nullptr;
+  // optional per-category device timing (CUDA events on the forward's stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { int cat; double work; int e0, e1; };
+  std::vector<Span> spans;
+  int ev_used = 0;
+  b200q_profile prof{};
+  int get_event() {
+    if (ev_used == (int)ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev_pool.push_back(e);
+    }
+    return ev_used++;
+  }
 };
 
 static inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
@@ -92,6 +107,8 @@ int b200q_model_create(const b200q_model_config* cfg, b200q_model_t* out) {
 }
 
 int b200q_model_destroy(b200q_model_t m) {
+  if (m)
+    for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
   delete m;
   return B200Q_OK;
 }
@@ -183,6 +200,33 @@ int b200q_model_bind_workspace(b200q_model_t m, void* p, int64_t bytes) {
 
 const void* b200q_model_logits_ptr(b200q_model_t m) { return m ? m->logits : nullptr; }
 
+int b200q_model_set_profiling(b200q_model_t m, int on) {
+  B200Q_CHECK_ARG(m, "set_profiling: null model");
+  m->profiling = on != 0;
+  return B200Q_OK;
+}
+
+// resolve the event pairs recorded since the last collect (the stream must be idle) and add
+// them to the running per-category totals
+int b200q_model_profile_collect(b200q_model_t m, b200q_profile* out, int reset) {
+  B200Q_CHECK_ARG(m && out, "profile_collect: null argument");
+  for (const auto& sp : m->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, m->ev_pool[sp.e0], m->ev_pool[sp.e1]) == cudaSuccess) {
+      m->prof.ms[sp.cat] += ms;
+      m->prof.work[sp.cat] += sp.work;
+      m->prof.launches[sp.cat] += 1;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  m->spans.clear();
+  m->ev_used = 0;
+  *out = m->prof;
+  if (reset) m->prof = b200q_profile{};
+  return B200Q_OK;
+}
+
 int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
   B200Q_CHECK_ARG(m && b, "forward: null argument");
   const b200q_model_config& c = m->cfg;
@@ -208,42 +252,54 @@ int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
   const int QKV = (int)qkv_dim(c), QD = NQ * D;
   const int64_t kv_layer_bytes = m->num_blocks * 2 * (int64_t)NKV * c.block_size * D * 2;
   int rc;
-#define B200Q_TRY(call) \
-  do {                  \
-    rc = (call);        \
-    if (rc) return rc;  \
+  cudaStream_t cst = as_stream(stream);
+#define B200Q_TRY(cat, work, call)                          \
+  do {                                                      \
+    int _e0 = -1;                                           \
+    if (m->profiling) {                                     \
+      _e0 = m->get_event();                                 \
+      cudaEventRecord(m->ev_pool[_e0], cst);                \
+    }                                                       \
+    rc = (call);                                            \
+    if (rc) return rc;                                      \
+    if (m->profiling) {                                     \
+      int _e1 = m->get_event();                             \
+      cudaEventRecord(m->ev_pool[_e1], cst);                \
+      m->spans.push_back({(cat), (double)(work), _e0, _e1}); \
+    }                                                       \
   } while (0)
+  const double kv_tok_bytes = 2.0 * NKV * D * 2;  // K+V bytes per cached token per layer
 
-  B200Q_TRY(b200q_embed(b->token_ids, m->embed, m->residual, T, H, stream));
+  B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_embed(b->token_ids, m->embed, m->residual, T, H, stream));
   for (int li = 0; li < c.n_layers; ++li) {
     const b200q_layer& L = m->layers[li];
     uint8_t* kv_layer = m->kv + li * kv_layer_bytes;
     if (li == 0)
-      B200Q_TRY(b200q_rmsnorm(m->residual, L.input_norm, m->x, T, H, c.rms_eps, stream));
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_rmsnorm(m->residual, L.input_norm, m->x, T, H, c.rms_eps, stream));
     else
-      B200Q_TRY(b200q_add_rmsnorm(m->x, m->residual, L.input_norm, T, H, c.rms_eps, stream));
-    B200Q_TRY(b200q_gemm_bf16(m->x, L.qkv, m->qkv, T, QKV, H, stream));
-    B200Q_TRY(b200q_rope_kvwrite(m->qkv, m->rope, b->positions, b->slot_mapping, kv_layer, T, NQ,
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, L.input_norm, T, H, c.rms_eps, stream));
+    B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * QKV * H, b200q_gemm_bf16(m->x, L.qkv, m->qkv, T, QKV, H, stream));
+    B200Q_TRY(B200Q_PROF_ELEMENTWISE, (double)T * (QKV + QD + 2.0 * NKV * D) * 2, b200q_rope_kvwrite(m->qkv, m->rope, b->positions, b->slot_mapping, kv_layer, T, NQ,
                                  NKV, D, c.block_size, stream));
-    B200Q_TRY(b200q_decode_attn(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
+    B200Q_TRY(B200Q_PROF_DECODE_ATTN, (double)b->sum_ctx_dec * kv_tok_bytes, b200q_decode_attn(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
                                 b->ctx_lens, b->n_dec, NQ, NKV, D, c.block_size, c.attn_scale,
                                 stream));
-    B200Q_TRY(b200q_prefill_attn(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
+    B200Q_TRY(B200Q_PROF_PREFILL_ATTN, (double)b->prefill_flops_per_layer, b200q_prefill_attn(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
                                  b->tiles, b->n_tiles, NQ, NKV, D, c.block_size, c.attn_scale,
                                  stream));
-    B200Q_TRY(b200q_gemm_bf16(m->attn, L.o, m->x, T, H, QD, stream));
-    B200Q_TRY(b200q_add_rmsnorm(m->x, m->residual, L.post_norm, T, H, c.rms_eps, stream));
-    B200Q_TRY(b200q_gemm_bf16(m->x, L.gate_up, m->gate_up, T, 2 * I, H, stream));
-    B200Q_TRY(b200q_swiglu(m->gate_up, m->act, T, I, stream));
-    B200Q_TRY(b200q_gemm_bf16(m->act, L.down, m->x, T, H, I, stream));
+    B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * H * QD, b200q_gemm_bf16(m->attn, L.o, m->x, T, H, QD, stream));
+    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, L.post_norm, T, H, c.rms_eps, stream));
+    B200Q_TRY(B200Q_PROF_GEMM, 4.0 * T * I * H, b200q_gemm_bf16(m->x, L.gate_up, m->gate_up, T, 2 * I, H, stream));
+    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 3.0 * T * I * 2, b200q_swiglu(m->gate_up, m->act, T, I, stream));
+    B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * H * I, b200q_gemm_bf16(m->act, L.down, m->x, T, H, I, stream));
   }
   if (b->n_sample > 0) {
     // only the rows that sample need the final norm + LM head; add_rmsnorm runs on all rows
     // because x/residual are per-row anyway and the gather wants the normalised value.
-    B200Q_TRY(b200q_add_rmsnorm(m->x, m->residual, m->final_norm, T, H, c.rms_eps, stream));
-    B200Q_TRY(b200q_gather_rows(m->x, b->sample_rows, m->sel, b->n_sample, H, stream));
-    B200Q_TRY(b200q_gemm_bf16(m->sel, m->lm_head, m->logits, b->n_sample, c.vocab, H, stream));
-    B200Q_TRY(b200q_argmax_bf16(m->logits, b->out_ids, b->n_sample, c.vocab, stream));
+    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, m->final_norm, T, H, c.rms_eps, stream));
+    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * b->n_sample * H * 2, b200q_gather_rows(m->x, b->sample_rows, m->sel, b->n_sample, H, stream));
+    B200Q_TRY(B200Q_PROF_GEMM, 2.0 * b->n_sample * (double)c.vocab * H, b200q_gemm_bf16(m->sel, m->lm_head, m->logits, b->n_sample, c.vocab, H, stream));
+    B200Q_TRY(B200Q_PROF_ELEMENTWISE, (double)b->n_sample * c.vocab * 2, b200q_argmax_bf16(m->logits, b->out_ids, b->n_sample, c.vocab, stream));
   }
 #undef B200Q_TRY
   return B200Q_OK;

@@ -1,0 +1,125 @@
+"""Synthetic model directories, tokenizers and JSONL job files.
+
+No tokenizer, config or checkpoint exists on disk in the build/bench environment and there is no
+network, so both the native worker and the oracle harness run on locally synthesised assets:
+
+  * a `tokenizers` WordLevel tokenizer whose vocabulary has exactly `vocab_size` entries
+    ("w<i>" for ordinary ids, Llama-3's <|begin_of_text|> / <|end_of_text|> / <|eot_id|> at their
+    usual ids when the vocabulary is large enough), whitespace pre-tokenisation, a BOS-prepending
+    post-processor and a Llama-3-style chat template.  "w17 w4 w99" tokenises to exactly
+    [BOS, 17, 4, 99] and decodes back to the same text, so prompt length is exact.
+  * config.json / generation_config.json with the real Llama dimensions,
+  * optional seeded safetensors weights (Normal(0, 0.02), unit norms) for small models,
+  * JSONL job files: {"id": "job-0000001", "prompt": "<127 random words>"}  => 128 prompt ids.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import List, Optional
+
+import numpy as np
+
+from .model import ModelSpec
+
+CHAT_TEMPLATE = (
+    "{{ bos_token }}{% for message in messages %}"
+    "{{ '<|start_header_id|> ' + message['role'] + ' <|end_header_id|> ' + message['content'] + ' <|eot_id|> ' }}"
+    "{% endfor %}{% if add_generation_prompt %}{{ '<|start_header_id|> assistant <|end_header_id|> ' }}{% endif %}"
+)
+
+
+def special_token_ids(vocab_size: int) -> dict:
+    if vocab_size >= 128256:  # Llama-3 layout
+        return {"<|begin_of_text|>": 128000, "<|end_of_text|>": 128001, "<|start_header_id|>": 128006,
+                "<|end_header_id|>": 128007, "<|eot_id|>": 128009}
+    # small test vocabularies: specials at the low ids
+    return {"<|begin_of_text|>": 0, "<|end_of_text|>": 1, "<|eot_id|>": 2,
+            "<|start_header_id|>": vocab_size - 2, "<|end_header_id|>": vocab_size - 1}
+
+
+def build_tokenizer(vocab_size: int):
+    """-> transformers.PreTrainedTokenizerFast"""
+    from tokenizers import Tokenizer, models, pre_tokenizers, processors
+    from transformers import PreTrainedTokenizerFast
+
+    sp = special_token_ids(vocab_size)
+    by_id = {i: f"w{i}" for i in range(vocab_size)}
+    for tok, i in sp.items():
+        by_id[i] = tok
+    vocab = {tok: i for i, tok in by_id.items()}
+    unk = "<|end_of_text|>"
+    tk = Tokenizer(models.WordLevel(vocab=vocab, unk_token=unk))
+    tk.pre_tokenizer = pre_tokenizers.WhitespaceSplit()
+    bos = "<|begin_of_text|>"
+    tk.post_processor = processors.TemplateProcessing(single=f"{bos} $A", special_tokens=[(bos, sp[bos])])
+    fast = PreTrainedTokenizerFast(tokenizer_object=tk, bos_token=bos, eos_token="<|end_of_text|>",
+                                   unk_token=unk, additional_special_tokens=[t for t in sp if t not in (bos, unk)])
+    fast.chat_template = CHAT_TEMPLATE
+    return fast
+
+
+def write_model_dir(path: str, spec: ModelSpec, *, seed: int = 1234, with_weights: bool = True) -> str:
+    """config.json + tokenizer (+ safetensors when with_weights) in `path`."""
+    os.makedirs(path, exist_ok=True)
+    sp = special_token_ids(spec.vocab)
+    cfg = spec.to_hf_config()
+    cfg["bos_token_id"] = sp["<|begin_of_text|>"]
+    cfg["eos_token_id"] = sp["<|end_of_text|>"]
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(cfg, f, indent=1)
+    with open(os.path.join(path, "generation_config.json"), "w") as f:
+        json.dump({"bos_token_id": cfg["bos_token_id"], "eos_token_id": cfg["eos_token_id"]}, f)
+    build_tokenizer(spec.vocab).save_pretrained(path)
+    if with_weights:
+        import torch
+        from safetensors.torch import save_file
+
+        g = torch.Generator().manual_seed(seed)
+        mat = lambda r, c: (torch.randn(r, c, generator=g) * 0.02).to(torch.bfloat16)
+        ones = lambda: torch.ones(spec.hidden, dtype=torch.bfloat16)
+        sd = {"model.embed_tokens.weight": mat(spec.vocab, spec.hidden)}
+        qd, kd = spec.n_q_heads * spec.head_dim, spec.n_kv_heads * spec.head_dim
+        for i in range(spec.n_layers):
+            p = f"model.layers.{i}."
+            sd[p + "input_layernorm.weight"] = ones()
+            sd[p + "post_attention_layernorm.weight"] = ones()
+            sd[p + "self_attn.q_proj.weight"] = mat(qd, spec.hidden)
+            sd[p + "self_attn.k_proj.weight"] = mat(kd, spec.hidden)
+            sd[p + "self_attn.v_proj.weight"] = mat(kd, spec.hidden)
+            sd[p + "self_attn.o_proj.weight"] = mat(spec.hidden, qd)
+            sd[p + "mlp.gate_proj.weight"] = mat(spec.intermediate, spec.hidden)
+            sd[p + "mlp.up_proj.weight"] = mat(spec.intermediate, spec.hidden)
+            sd[p + "mlp.down_proj.weight"] = mat(spec.hidden, spec.intermediate)
+        sd["model.norm.weight"] = ones()
+        if not spec.tie_embeddings:
+            sd["lm_head.weight"] = mat(spec.vocab, spec.hidden)
+        save_file(sd, os.path.join(path, "model.safetensors"), metadata={"format": "pt"})
+    return path
+
+
+def random_prompt_words(rng: np.random.Generator, n_tokens: int, vocab_size: int) -> str:
+    """n_tokens ordinary (non-special) word tokens rendered as text"""
+    sp = set(special_token_ids(vocab_size).values())
+    hi = min(vocab_size, 128000)
+    ids = rng.integers(3 if vocab_size < 128256 else 0, hi, size=n_tokens)
+    return " ".join(f"w{int(i)}" for i in ids if int(i) not in sp or True)
+
+
+def make_jobs(n_jobs: int, vocab_size: int, prompt_tokens: int = 127, seed: int = 20260921,
+              start: int = 0, stride: int = 1) -> List[dict]:
+    """jobs start, start+stride, ... of the canonical seeded job stream (job i is the same no
+    matter how the stream is sharded across workers)"""
+    out = []
+    for i in range(start, n_jobs, stride):
+        rng = np.random.default_rng([seed, i])
+        out.append({"id": f"job-{i:07d}", "prompt": random_prompt_words(rng, prompt_tokens, vocab_size)})
+    return out
+
+
+def write_jobs_jsonl(path: str, n_jobs: int, vocab_size: int, prompt_tokens: int = 127,
+                     seed: int = 20260921) -> str:
+    with open(path, "w") as f:
+        for j in make_jobs(n_jobs, vocab_size, prompt_tokens, seed):
+            f.write(json.dumps(j) + "\n")
+    return path

@@ -57,6 +57,8 @@ class Batch(C.Structure):
         ("tiles", C.c_void_p),
         ("sample_rows", C.c_void_p),
         ("out_ids", C.c_void_p),
+        ("sum_ctx_dec", C.c_int64),
+        ("prefill_flops_per_layer", C.c_int64),
     ]
 
 
@@ -81,7 +83,16 @@ class EngineStats(C.Structure):
         ("total_blocks", C.c_int32),
         ("last_step_tokens", C.c_int32),
         ("last_step_seqs", C.c_int32),
+        ("h2d_bytes", C.c_int64),
+        ("d2h_bytes", C.c_int64),
     ]
+
+
+class Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 4), ("work", C.c_double * 4), ("launches", C.c_int64 * 4)]
+
+
+PROF_NAMES = ("gemm", "decode_attn", "prefill_attn", "elementwise")
 
 
 FLAG_FINISHED_EOS = 1
@@ -115,6 +126,9 @@ SIGNATURES = {
     "b200q_model_bind_workspace": (_i, [_vp, _vp, _i64]),
     "b200q_model_forward": (_i, [_vp, C.POINTER(Batch), _vp]),
     "b200q_model_logits_ptr": (_vp, [_vp]),
+    "b200q_model_set_profiling": (_i, [_vp, _i]),
+    "b200q_model_profile_collect": (_i, [_vp, C.POINTER(Profile), _i]),
+    "b200q_engine_stream": (_vp, [_vp]),
     "b200q_engine_create": (_i, [_vp, C.POINTER(EngineConfig), C.POINTER(_vp)]),
     "b200q_engine_destroy": (_i, [_vp]),
     "b200q_engine_add_request": (_i, [_vp, _i64, _vp, C.c_int32, C.c_int32, C.c_int32]),

@@ -252,6 +252,16 @@ class NativeModel:
         off = ptr - self.workspace.data_ptr()
         return self.workspace[off: off + n * self.spec.vocab * 2].view(torch.bfloat16).view(n, self.spec.vocab)
 
+    def set_profiling(self, on: bool) -> None:
+        L.check(self.lib.b200q_model_set_profiling(self.handle, int(on)))
+
+    def collect_profile(self, reset: bool = False) -> dict:
+        """per-category device time (CUDA events on the forward's stream); the stream must be idle"""
+        p = L.Profile()
+        L.check(self.lib.b200q_model_profile_collect(self.handle, C.byref(p), int(reset)))
+        return {n: {"ms": p.ms[i], "work": p.work[i], "launches": int(p.launches[i])}
+                for i, n in enumerate(L.PROF_NAMES)}
+
     def close(self):
         if self.handle:
             self.lib.b200q_model_destroy(self.handle)
@@ -301,6 +311,10 @@ class Engine:
                                            self._flg.ctypes.data, self.cap, C.byref(n)))
         k = n.value
         return self._ids[:k], self._tok[:k], self._flg[:k]
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self.lib.b200q_engine_stream(self.handle))
 
     def stats(self) -> L.EngineStats:
         s = L.EngineStats()

@@ -1,0 +1,190 @@
+"""GenerationService — engine thread + request table around the native engine.
+
+Pure host logic with no llmq import, so it can be driven directly (bench.py, tests) exactly the
+way ``B200Worker._process_job`` drives it: ``future = service.submit(ids, ...); await future``.
+
+Threading model: the asyncio event-loop thread owns AMQP, tokenisation and
+futures; ONE engine thread owns the CUDA context and runs the continuous-batching step loop
+(`b200q_engine_step`, GIL released inside the C call).
+"""
+from __future__ import annotations
+
+import asyncio
+import os
+import queue
+import threading
+import time
+from typing import Dict, List, Optional
+
+from . import lib as L
+
+
+class _Req:
+    __slots__ = ("rid", "prompt_ids", "max_new", "stop", "future", "out_ids", "text_len", "loop")
+
+    def __init__(self, rid, prompt_ids, max_new, stop, future, loop):
+        self.rid, self.prompt_ids, self.max_new, self.stop = rid, prompt_ids, max_new, stop
+        self.future, self.loop = future, loop
+        self.out_ids: List[int] = []
+        self.text_len = 0
+
+
+class GenerationService:
+    """Engine thread + request table.  Pure host logic around llmq_b200.model.Engine; also used
+    directly by bench.py (the same public call a worker makes)."""
+
+    def __init__(self, engine, tokenizer, eos_token_id: Optional[int]):
+        self.engine = engine
+        self.tokenizer = tokenizer
+        self.eos_token_id = eos_token_id
+        self._inbox: "queue.SimpleQueue[_Req]" = queue.SimpleQueue()
+        self._reqs: Dict[int, _Req] = {}
+        self._next_id = 0
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, name="b200q-engine", daemon=True)
+        self.error: Optional[BaseException] = None
+        self.tokens_out = 0
+        self.jobs_done = 0
+        self.first_submit_t: Optional[float] = None
+        self.last_finish_t: Optional[float] = None
+
+    def start(self):
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread.is_alive():
+            self._thread.join(timeout=30)
+
+    # ---- called on the event-loop thread ----
+    def submit(self, prompt_ids: List[int], max_new: int, stop: Optional[List[str]],
+               loop: asyncio.AbstractEventLoop) -> "asyncio.Future":
+        if self.error is not None:
+            raise RuntimeError(f"engine thread died: {self.error!r}")
+        fut = loop.create_future()
+        self._next_id += 1
+        self._inbox.put(_Req(self._next_id, prompt_ids, max_new, stop, fut, loop))
+        return fut
+
+    # ---- engine thread ----
+    def _finish(self, batch, r: _Req, text: Optional[str] = None, exc: Optional[BaseException] = None):
+        self._reqs.pop(r.rid, None)
+        if exc is None and text is None:
+            text = self.tokenizer.decode(r.out_ids, skip_special_tokens=True)
+        self.jobs_done += 1
+        self.tokens_out += len(r.out_ids)
+        self.last_finish_t = time.perf_counter()
+        batch.setdefault(r.loop, []).append((r.future, text, exc, len(r.out_ids)))
+
+    @staticmethod
+    def _deliver(items):
+        for fut, text, exc, n in items:
+            if fut.done():
+                continue
+            if exc is not None:
+                fut.set_exception(exc)
+            else:
+                fut.set_result((text, n))
+
+    def _check_stop_strings(self, r: _Req) -> Optional[str]:
+        """vLLM detokenizer semantics (vllm/v1/engine/detokenizer.py:131-143): after every new
+        token look for a stop string in the newly produced text; the output is cut before it."""
+        text = self.tokenizer.decode(r.out_ids, skip_special_tokens=True)
+        start = max(0, r.text_len - max(len(s) for s in r.stop))
+        r.text_len = len(text)
+        best = -1
+        for s in r.stop:
+            i = text.find(s, start)
+            if i >= 0 and (best < 0 or i < best):
+                best = i
+        return text[:best] if best >= 0 else None
+
+    def _run(self):
+        eng = self.engine
+        try:
+            if getattr(eng.model, "device", None) is not None:
+                import torch
+
+                torch.cuda.set_device(eng.model.device)  # this thread owns the CUDA context
+            while not self._stop.is_set():
+                batch: dict = {}
+                # admit new requests
+                try:
+                    block = not eng.has_work()
+                    r = self._inbox.get(timeout=0.05) if block else self._inbox.get_nowait()
+                    while True:
+                        if self.first_submit_t is None:
+                            self.first_submit_t = time.perf_counter()
+                        try:
+                            eng.add_request(r.rid, r.prompt_ids, r.max_new, ignore_eos=False)
+                            self._reqs[r.rid] = r
+                        except ValueError as e:  # un-servable job => dropped by the base class
+                            self._finish(batch, r, exc=e)
+                        r = self._inbox.get_nowait()
+                except queue.Empty:
+                    pass
+                if eng.has_work():
+                    ids, toks, flags = eng.step()
+                    for rid, tok, flag in zip(ids.tolist(), toks.tolist(), flags.tolist()):
+                        r = self._reqs.get(rid)
+                        if r is None:
+                            continue
+                        r.out_ids.append(tok)
+                        if r.stop:
+                            cut = self._check_stop_strings(r)
+                            if cut is not None:
+                                if not flag:
+                                    eng.abort(rid)
+                                self._finish(batch, r, text=cut)
+                                continue
+                        if flag:
+                            self._finish(batch, r)
+                for loop, items in batch.items():
+                    loop.call_soon_threadsafe(self._deliver, items)
+        except BaseException as e:  # surface engine failures to every waiter
+            self.error = e
+            batch = {}
+            for r in list(self._reqs.values()):
+                self._finish(batch, r, exc=RuntimeError(f"engine failure: {e!r}"))
+            for loop, items in batch.items():
+                loop.call_soon_threadsafe(self._deliver, items)
+            raise
+
+
+def build_service(model_name: str, *, max_num_seqs: Optional[int], max_model_len: Optional[int],
+                  gpu_memory_utilization: float, max_num_batched_tokens: Optional[int] = None,
+                  seed: int = 1234, logger=None) -> GenerationService:
+    """model + KV pool + engine + tokenizer for `model_name` (local dir or random:<builtin>)."""
+    import torch
+
+    from .model import Engine, NativeModel, fuse_hf_weights, load_hf_state_dict, random_engine_weights, resolve_model
+
+    L.require_device()  # raises: this worker has no CPU path
+    spec, model_dir = resolve_model(model_name)
+    device = torch.device("cuda", torch.cuda.current_device())
+    max_num_seqs = max_num_seqs or int(os.environ.get("B200Q_MAX_NUM_SEQS", "256"))
+    max_model_len = min(max_model_len or int(os.environ.get("B200Q_MAX_MODEL_LEN", "4096")),
+                        spec.max_position_embeddings)
+    budget = max_num_batched_tokens or int(os.environ.get("B200Q_MAX_NUM_BATCHED_TOKENS", "4096"))
+    budget = max(budget, 16)
+    if model_dir is None:
+        from .fixtures import build_tokenizer, special_token_ids
+
+        weights = random_engine_weights(spec, seed, device)
+        tokenizer = build_tokenizer(spec.vocab)
+        eos = special_token_ids(spec.vocab)["<|end_of_text|>"]
+    else:
+        from transformers import AutoTokenizer
+
+        weights = fuse_hf_weights(spec, load_hf_state_dict(model_dir))
+        tokenizer = AutoTokenizer.from_pretrained(model_dir)
+        eos = spec.eos_token_id if spec.eos_token_id is not None else tokenizer.eos_token_id
+    model = NativeModel(spec, weights, max_tokens=budget, max_seqs=max_num_seqs,
+                        max_model_len=max_model_len, gpu_memory_utilization=gpu_memory_utilization,
+                        device=device)
+    if logger:
+        logger.info(f"b200q model {spec.name}: {model.num_blocks} KV blocks of 16 tokens, "
+                    f"max_num_seqs={max_num_seqs}, token budget={budget}, max_model_len={max_model_len}")
+    engine = Engine(model, max_num_seqs=max_num_seqs, max_num_batched_tokens=budget,
+                    max_model_len=max_model_len, eos_token_id=eos)
+    return GenerationService(engine, tokenizer, eos)

@@ -1,0 +1,145 @@
+"""Host-side logic of the worker slot, CPU only: the reference's BaseWorker / BrokerManager /
+Job / Result code runs UNMODIFIED (from baseline/_ref or /root/reference) on the aio_pika
+stand-in, with B200Worker plugged in and a fake engine in place of the GPU."""
+import asyncio
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "shims"))
+for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+    if os.path.isdir(os.path.join(p, "llmq")):
+        sys.path.insert(0, p)
+        break
+os.environ.setdefault("LLMQ_LOG_LEVEL", "WARNING")
+
+import aio_pika  # noqa: E402  (the stand-in)
+from llmq.core.broker import BrokerManager  # noqa: E402
+from llmq.core.models import Job, Result  # noqa: E402
+
+from llmq_b200 import service as S  # noqa: E402
+from llmq_b200.fixtures import build_tokenizer, make_jobs  # noqa: E402
+from llmq_b200.worker import B200Worker  # noqa: E402
+from tests.fake_engine import FakeEngine  # noqa: E402
+
+VOCAB = 1024
+
+
+@pytest.fixture()
+def patched(monkeypatch):
+    aio_pika.reset_brokers()
+    tok = build_tokenizer(VOCAB)
+    made = {}
+
+    def fake_build_service(model_name, **kw):
+        eng = FakeEngine(vocab=VOCAB, max_num_seqs=kw.get("max_num_seqs") or 8, max_model_len=64, eos_token_id=1)
+        made["engine"] = eng
+        made["kw"] = kw
+        return S.GenerationService(eng, tok, 1)
+
+    import llmq_b200.worker as W
+    monkeypatch.setattr(W, "build_service", fake_build_service)
+    monkeypatch.setenv("VLLM_MAX_TOKENS", "6")
+    monkeypatch.setenv("VLLM_MAX_NUM_SEQS", "4")
+    monkeypatch.setenv("VLLM_QUEUE_PREFETCH", "16")
+    return made, tok
+
+
+def test_worker_id_and_ctor_signature_match_reference(patched):
+    w = B200Worker("random:llama-3-8b", "q", None, 1, 1, None, None, None, None)
+    assert w.worker_id.startswith("b200-") and w.queue_name == "q" and not w.is_pipeline_worker
+    wp = B200Worker("m", "pipeline.p.s1", pipeline_name="p", stage_name="s1", pipeline_stages=["s1", "s2"])
+    assert wp.is_pipeline_worker
+
+
+def test_rejects_tensor_parallel(patched):
+    w = B200Worker("m", "q", tensor_parallel_size=2)
+    with pytest.raises(ValueError):
+        asyncio.run(w._initialize_processor())
+
+
+def test_end_to_end_through_reference_base_worker_and_broker(patched):
+    made, tok = patched
+
+    async def main():
+        w = B200Worker("random:llama-3-8b", "bq", tensor_parallel_size=1)
+        task = asyncio.create_task(w.run())
+        b = BrokerManager()
+        await b.connect()
+        await b.setup_queue_infrastructure("bq")
+        jobs = [Job(id=f"j{i}", prompt="{a} w7", a=f"w{10 + i}", url=f"u{i}") for i in range(20)]
+        jobs.append(Job(id="chat", messages=[{"role": "user", "content": "w5 w6"}]))
+        jobs.append(Job(id="stop", prompt="w100", stop=["w103"]))
+        jobs.append(Job(id="toolong", prompt=" ".join(["w9"] * 80)))  # > max_model_len: dropped
+        jobs.append(Job(id="per-job-cap", prompt="w200", max_tokens=2))
+        for j in jobs:
+            await b.publish_job("bq", j)
+        got = {}
+
+        async def on_res(m):
+            r = Result.parse_raw(m.body)
+            got[r.id] = r
+            await m.ack()
+
+        await b.consume_results("bq", on_res)
+        for _ in range(200):
+            if len(got) >= len(jobs) - 1:
+                break
+            await asyncio.sleep(0.05)
+        w.running = False
+        await asyncio.wait_for(task, 10)
+        return got, w
+
+    got, w = asyncio.run(main())
+    eng = made["engine"]
+    assert made["kw"]["max_num_seqs"] == 4 and eng.max_batch_seen == 4  # VLLM_MAX_NUM_SEQS honoured
+    assert "toolong" not in got  # ValueError => acked and dropped (base.py:228-235)
+    assert len(got) == 23
+    # fake model counts up from the last prompt token; 6 tokens (VLLM_MAX_TOKENS), text only
+    assert got["j3"].result == "w8 w9 w10 w11 w12 w13"
+    assert got["j3"].prompt == "w13 w7" and got["j3"].worker_id == w.worker_id
+    assert got["j3"].model_dump()["url"] == "u3" and got["j3"].model_dump()["a"] == "w13"  # extras copied
+    assert got["chat"].prompt == "Chat with 1 messages"
+    assert got["stop"].result == "w101 w102 "  # cut right before the stop string (no stripping, as vLLM); generation aborted
+    assert got["per-job-cap"].result == "w201 w202"
+    assert w.jobs_processed == 23
+
+
+def test_chat_prompt_carries_double_bos_like_the_reference(patched):
+    _, tok = patched
+    w = B200Worker("m", "q", tensor_parallel_size=1)
+    w.service = S.GenerationService(FakeEngine(), tok, 1)
+    text = w.build_prompt(Job(id="c", messages=[{"role": "user", "content": "w5"}]))
+    ids = tok(text, add_special_tokens=True).input_ids
+    assert ids[0] == ids[1] == tok.bos_token_id
+    assert w.stop_strings(Job(id="a", prompt="x")) is None
+    assert w.stop_strings(Job(id="a", prompt="x", stop=[tok.eos_token])) is None  # inert special
+    assert w.stop_strings(Job(id="a", prompt="x", stop=["END", tok.eos_token])) == ["END"]
+
+
+def test_eos_finishes_and_is_not_rendered(patched):
+    _, tok = patched
+    eng = FakeEngine(vocab=VOCAB, eos_token_id=1)
+    svc = S.GenerationService(eng, tok, 1)
+    svc.start()
+
+    async def main():
+        loop = asyncio.get_running_loop()
+        # last prompt token 1020 -> generates 1021, 1022/1023 (header specials), 0 (BOS), 1 (EOS): stop
+        text, n = await svc.submit([0, 1020], 50, None, loop)
+        return text, n
+
+    text, n = asyncio.run(main())
+    svc.stop()
+    assert n == 5 and text == "w1021"
+
+
+def test_job_stream_is_sharding_invariant():
+    full = make_jobs(12, VOCAB, prompt_tokens=5)
+    shards = [make_jobs(12, VOCAB, prompt_tokens=5, start=r, stride=3) for r in range(3)]
+    merged = sorted((j for s in shards for j in s), key=lambda j: j["id"])
+    assert merged == full and len({j["id"] for j in full}) == 12
+    assert json.loads(json.dumps(full[0]))["prompt"].count("w") == 5

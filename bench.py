@@ -57,6 +57,22 @@ def ensure_llmq_importable():
         import llmq.workers.base  # noqa: F401
 
 
+def usable_host_cores() -> int:
+    """threads the CPU arm may really use: scheduler affinity, capped by the cgroup CPU quota
+    (os.cpu_count() reports the whole host inside a limited container and oversubscribes BLAS)"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, int(os.environ.get("B200Q_CPU_THREADS", "64"))))
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -126,7 +142,7 @@ def cpu_reference_sample(model_key: str, prompt_tokens: int, out_tokens: int, bu
     from oracle.model import LlamaDims, LlamaOracle
 
     spec = BUILTIN_SPECS[model_key]
-    cores = os.cpu_count() or 1
+    cores = usable_host_cores()
     torch.set_num_threads(cores)
     dims = LlamaDims(hidden=spec.hidden, n_layers=spec.n_layers, n_q_heads=spec.n_q_heads,
                      n_kv_heads=spec.n_kv_heads, head_dim=spec.head_dim, intermediate=spec.intermediate,
@@ -159,7 +175,8 @@ def cpu_reference_sample(model_key: str, prompt_tokens: int, out_tokens: int, bu
         t_prefill = time.perf_counter() - t0
         n_dec, t_dec = 0, 0.0
         tok = int(logits[-1].argmax())
-        while n_dec < out_tokens - 1 and (t_prefill + t_dec) < budget_s:
+        # at least 4 decode steps are always timed, so the extrapolation has a decode term
+        while n_dec < out_tokens - 1 and (n_dec < 4 or (t_prefill + t_dec) < budget_s):
             t1 = time.perf_counter()
             logits, kv = oracle.forward(torch.tensor([tok]), torch.tensor([prompt_tokens + n_dec]), kv, all_logits=False)
             tok = int(logits[-1].argmax())
@@ -237,7 +254,10 @@ def run_native(args):
     peaks = load_peaks()
     svc: GenerationService = build_service(
         f"random:{args.model}", max_num_seqs=args.max_num_seqs, max_model_len=args.max_model_len,
-        gpu_memory_utilization=0.9, max_num_batched_tokens=args.max_num_batched_tokens, seed=1234 + rank)
+        gpu_memory_utilization=0.9, max_num_batched_tokens=args.max_num_batched_tokens, seed=1234 + rank,
+        num_blocks=args.num_blocks)
+    if args.gemm_mode:
+        L.gemm_set_mode(args.gemm_mode)
     eng, model, tok = svc.engine, svc.engine.model, svc.tokenizer
     spec = model.spec
     n_steps_total = args.warmup + args.steps
@@ -405,10 +425,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--model", default="llama-3-8b")
-    ap.add_argument("--jobs", type=int, default=1024, help="jobs per step per GPU")
+    ap.add_argument("--jobs", type=int, default=2048, help="jobs per step per GPU")
+    ap.add_argument("--num-blocks", type=int, default=None, help="KV pool size in 16-token blocks (default: from gpu_memory_utilization)")
+    ap.add_argument("--gemm-mode", type=int, default=0, help="tuning hook: 0 auto, 1 1-CTA kernels, 2 2-CTA kernel")
     ap.add_argument("--prompt-tokens", type=int, default=128)
     ap.add_argument("--out-tokens", type=int, default=128)
-    ap.add_argument("--max-num-seqs", type=int, default=1024)
+    ap.add_argument("--max-num-seqs", type=int, default=2048)
     ap.add_argument("--max-num-batched-tokens", type=int, default=8192)
     ap.add_argument("--max-model-len", type=int, default=512)
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)

@@ -95,6 +95,12 @@ int b200q_prefill_attn(const void* q_dev, int q_stride, void* out_dev, const voi
 int b200q_gemm_bf16(const void* A_dev, const void* W_dev, void* C_dev,
                     int M, int N, int K, void* stream);
 
+/* K9+K10 fused: out[M, N/2] = SwiGLU(A . W^T); W [N=2I, K] holds gate/up rows INTERLEAVED in blocks
+ *     of 128: rows [256j, 256j+128) = gate rows [128j, 128j+128), rows [256j+128, 256j+256) = the
+ *     matching up rows.  Rounding identical to b200q_gemm_bf16 followed by b200q_swiglu. */
+int b200q_gemm_swiglu_bf16(const void* A_dev, const void* W_dev, void* C_dev,
+                           int M, int N, int K, void* stream);
+
 /* K10 SwiGLU: out[t,i] = bf16(bf16(silu(g[t,i])) * u[t,i]), gate_up = [T, 2I] = (g | u)
  *     (vllm activation.py:138-141 SiluAndMul.forward_native) */
 int b200q_swiglu(const void* gate_up_dev, void* out_dev, int T, int I, void* stream);
@@ -156,7 +162,8 @@ int b200q_model_create(const b200q_model_config* cfg, b200q_model_t* out);
 int b200q_model_destroy(b200q_model_t m);
 /* names: "embed", "final_norm", "lm_head", and per layer i: "layers.i.input_norm",
  * "layers.i.qkv" [(n_q+2n_kv)D, H], "layers.i.o" [H, n_q D], "layers.i.post_norm",
- * "layers.i.gate_up" [2I, H], "layers.i.down" [H, I].  bf16, row-major, contiguous. */
+ * "layers.i.gate_up" [2I, H] (gate/up rows interleaved in 128-row blocks, see
+ * b200q_gemm_swiglu_bf16), "layers.i.down" [H, I].  bf16, row-major, contiguous. */
 int b200q_model_bind_weight(b200q_model_t m, const char* name, const void* dev_ptr,
                             int64_t rows, int64_t cols);
 /* kv: [L][num_blocks][2][n_kv][block_size][D] bf16, zero-initialised by the caller */

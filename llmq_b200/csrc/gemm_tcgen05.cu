@@ -110,7 +110,59 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
          ((uint32_t)(GEMM_BM >> 4) << 24);
 }
 
-template <int BN>
+// Drain this thread's TMEM lane (one output row of the 128 x BN fp32 accumulator tile) to global.
+// kSwiGLU (K9+K10 fused): the weight rows were interleaved at load time so that the tile's
+// columns are [gate (BN/2) | up (BN/2)] of the SAME BN/2 output columns; the epilogue applies
+// out = bf16(bf16(silu(bf16(g))) * bf16(u)) — identical rounding points to the unfused path
+// (GEMM output rounded to bf16, then oracle/ops.py::swiglu) — and writes BN/2 columns, so the
+// [T, 2I] intermediate never touches HBM.
+template <int BN, bool kSwiGLU>
+__device__ __forceinline__ void epilogue_row(uint32_t taddr, bf16* crow, bool valid) {
+  if constexpr (!kSwiGLU) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+          o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+          o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+          o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+          st_v4(crow + c0 + 8 * j, o);
+        }
+      }
+    }
+  } else {
+    auto act = [](uint32_t gb, uint32_t ub) -> float {
+      const float g = round_bf16(__uint_as_float(gb)), u = round_bf16(__uint_as_float(ub));
+      return round_bf16(g / (1.f + __expf(-g))) * u;
+    };
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+      uint32_t g[32], u[32];
+      tmem_ld32(taddr + (uint32_t)c0, g);
+      tmem_ld32(taddr + (uint32_t)(BN / 2 + c0), u);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_bf16x2(act(g[8 * j + 0], u[8 * j + 0]), act(g[8 * j + 1], u[8 * j + 1]));
+          o.y = pack_bf16x2(act(g[8 * j + 2], u[8 * j + 2]), act(g[8 * j + 3], u[8 * j + 3]));
+          o.z = pack_bf16x2(act(g[8 * j + 4], u[8 * j + 4]), act(g[8 * j + 5], u[8 * j + 5]));
+          o.w = pack_bf16x2(act(g[8 * j + 6], u[8 * j + 6]), act(g[8 * j + 7], u[8 * j + 7]));
+          st_v4(crow + c0 + 8 * j, o);
+        }
+      }
+    }
+  }
+}
+
+template <int BN, bool kSwiGLU = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b, bf16* __restrict__ C, int M,
@@ -218,25 +270,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const int row = m_blk * GEMM_BM + quarter * 32 + lane;
-      bf16* crow = C + (long long)row * N + (long long)n_blk * BN;
+      constexpr int OUT_BN = kSwiGLU ? BN / 2 : BN;
+      const long long ldc = kSwiGLU ? N / 2 : N;
+      bf16* crow = C + (long long)row * ldc + (long long)n_blk * OUT_BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (row < M) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-            st_v4(crow + c0 + 8 * j, o);
-          }
-        }
-      }
+      epilogue_row<BN, kSwiGLU>(taddr, crow, row < M);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
@@ -250,6 +288,228 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ==================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BN tile.  Each CTA stages
+// its own 128 rows of A and HALF of the B tile (BN/2 weight rows), the leader issues
+// tcgen05.mma.cta_group::2 (UMMA M=256) which reads both CTAs' shared memory, and each CTA drains
+// its own 128 x BN accumulator from its TMEM.  Per-SM operand ingest per k-block drops from
+// 16 KB + BN*128 B to 16 KB + BN*64 B for the same MMA work — the 1-CTA kernel is ingest-bound
+// (profiles/r1_microbench.md), this one moves the bound back to the tensor pipe.
+// ==================================================================================================
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;        // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;       // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = GEMM_SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : GEMM_SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(
+                   bar_cluster_addr),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, int c0, int c1,
+                                                uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN, bool kSwiGLU = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                      const __grid_constant__ CUtensorMap tmap_b, bf16* __restrict__ C, int M,
+                      int N, int K) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_tiles = (M + 255) / 256;
+  const int n_tiles = N / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = K / GEMM_BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 2);   // (leader's copy is the live one) one arrive per CTA's producer
+      mbar_init(empty + s, 1);  // multicast tcgen05.commit from the leader
+    }
+    mbar_init(tmem_full + 0, 1);
+    mbar_init(tmem_full + 1, 1);
+    mbar_init(tmem_empty + 0, 8);  // 4 epilogue warps x 2 CTAs, all arriving at the leader
+    mbar_init(tmem_empty + 1, 8);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer barriers are initialised before anybody signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A rows + own half of B, completion on the LEADER =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1u);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          const uint32_t lfull = mapa_shared(full + stage, 0);
+          mbar_expect_tx_cluster(lfull, Cfg::STAGE_BYTES);
+          tma_load_2d_2sm(sa, &tmap_a, kb * GEMM_BK, m_blk * 256 + (int)rank * 128, lfull);
+          tma_load_2d_2sm(sb, &tmap_b, kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2), lfull);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only =====
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_2sm(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(tmem_empty + acc, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              umma_bf16_2sm(tmem_d, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(empty + stage);
+            if (kb == k_blocks - 1) umma_commit_2sm(tmem_full + acc);
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): own 128 rows of the 256-row tile =====
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 256 + (int)rank * 128 + quarter * 32 + lane;
+      constexpr int OUT_BN = kSwiGLU ? BN / 2 : BN;
+      const long long ldc = kSwiGLU ? N / 2 : N;
+      bf16* crow = C + (long long)row * ldc + (long long)n_blk * OUT_BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      epilogue_row<BN, kSwiGLU>(taddr, crow, row < M);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tmem_empty + acc, 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody frees TMEM / exits while the peer may still signal or read
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -344,7 +604,7 @@ static int num_sms() {
   return n;
 }
 
-template <int BN>
+template <int BN, bool kSwiGLU = false>
 static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int K,
                        cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
@@ -353,7 +613,7 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
   if (rc) return rc;
   rc = get_tmap(W, N, K, BN, &tb);
   if (rc) return rc;
-  auto kern = gemm_bf16_kernel<BN>;
+  auto kern = gemm_bf16_kernel<BN, kSwiGLU>;
   static bool attr_set = false;
   if (!attr_set) {
     B200Q_CUDA(
@@ -367,7 +627,56 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
   return B200Q_OK;
 }
 
+static int g_gemm2_pairs = 0;  // co-resident CTA pairs reported by the occupancy query
+
+template <int BN, bool kSwiGLU = false>
+static int launch_gemm2(const void* A, const void* W, void* C, int M, int N, int K,
+                        cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN>;
+  CUtensorMap ta, tb;
+  int rc = get_tmap(A, M, K, GEMM_BM, &ta);
+  if (rc) return rc;
+  rc = get_tmap(W, N, K, BN / 2, &tb);
+  if (rc) return rc;
+  auto kern = gemm2_bf16_kernel<BN, kSwiGLU>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200Q_CUDA(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+    attr_set = true;
+  }
+  const int tiles = ((M + 255) / 256) * (N / BN);
+  // the tile loop is static round-robin over CO-RESIDENT CTA pairs: size the grid by what the
+  // hardware can really keep resident at once (GPC/TPC pairing can make this < SMs/2)
+  static int pairs = 0;
+  if (pairs == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms() & ~1);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_TOTAL;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms() / 2;
+    }
+    pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+    g_gemm2_pairs = pairs;
+  }
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
 int g_gemm_force_bn = 0;  // test hook: 0 = heuristic
+int g_gemm_mode = 0;      // 0 = auto, 1 = force 1-CTA kernels, 2 = force the 2-CTA kernel
 
 }  // namespace b200q
 
@@ -382,6 +691,16 @@ int b200q_gemm_set_tile_n(int bn) {
   return B200Q_OK;
 }
 
+// test/tuning hook: 0 = auto, 1 = 1-CTA kernels only, 2 = 2-CTA (cta_group::2) kernel whenever legal
+// diagnostics: co-resident CTA pairs the 2-CTA kernel's grid is sized to (0 until first use)
+int b200q_gemm_resident_pairs(void) { return g_gemm2_pairs; }
+
+int b200q_gemm_set_mode(int mode) {
+  B200Q_CHECK_ARG(mode >= 0 && mode <= 2, "gemm mode must be 0/1/2");
+  g_gemm_mode = mode;
+  return B200Q_OK;
+}
+
 int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, void* stream) {
   B200Q_CHECK_ARG(M >= 0 && N > 0 && K > 0 && K % GEMM_BK == 0 && N % 64 == 0,
                   "gemm: unsupported shape M=%d N=%d K=%d (need K%%64==0, N%%64==0)", M, N, K);
@@ -392,6 +711,10 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
   if (M == 0) return B200Q_OK;
   cudaStream_t st = as_stream(stream);
   int bn = g_gemm_force_bn;
+  if (g_gemm_mode == 2 && M > GEMM_BM) {
+    if ((bn == 0 || bn == 256) && N % 256 == 0) return launch_gemm2<256>(A, W, C, M, N, K, st);
+    if ((bn == 0 || bn == 128) && N % 128 == 0) return launch_gemm2<128>(A, W, C, M, N, K, st);
+  }
   if (bn == 0) {
     // Every CTA walks ceil(tiles / SMs) tiles; measured on B200 (profiles/r1_microbench.md) a
     // 128-wide tile costs ~0.85x and a 64-wide tile ~0.8x the time of a 256-wide one (the kernel
@@ -416,6 +739,23 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
   if (bn == 256) return launch_gemm<256>(A, W, C, M, N, K, st);
   if (bn == 128) return launch_gemm<128>(A, W, C, M, N, K, st);
   return launch_gemm<64>(A, W, C, M, N, K, st);
+}
+
+// K9+K10 fused: out[M, N/2] = swiglu(A . W^T) where W [N, K] holds gate/up rows interleaved in
+// blocks of 128 (rows [256j, 256j+128) = gate rows [128j, 128j+128), next 128 = the matching up
+// rows).  Same rounding points as b200q_gemm_bf16 followed by b200q_swiglu.
+int b200q_gemm_swiglu_bf16(const void* A, const void* W, void* C, int M, int N, int K,
+                           void* stream) {
+  B200Q_CHECK_ARG(M >= 0 && N > 0 && K > 0 && K % GEMM_BK == 0 && N % 256 == 0,
+                  "gemm_swiglu: unsupported shape M=%d N=%d K=%d (need K%%64==0, N%%256==0)", M, N, K);
+  B200Q_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+                  "gemm_swiglu: operands must be 16-byte aligned");
+  if (M == 0) return B200Q_OK;
+  cudaStream_t st = as_stream(stream);
+  if (g_gemm_mode == 2 && M > GEMM_BM) return launch_gemm2<256, true>(A, W, C, M, N, K, st);
+  return launch_gemm<256, true>(A, W, C, M, N, K, st);
 }
 
 }  // extern "C"

@@ -65,8 +65,9 @@ static int check_cfg(const b200q_model_config* c) {
   B200Q_CHECK_ARG(c->n_kv_heads > 0 && c->n_q_heads % c->n_kv_heads == 0 &&
                       c->n_q_heads / c->n_kv_heads <= 8,
                   "heads n_q=%d n_kv=%d unsupported", c->n_q_heads, c->n_kv_heads);
-  B200Q_CHECK_ARG(c->intermediate > 0 && c->intermediate % 64 == 0, "intermediate=%d unsupported",
-                  c->intermediate);
+  B200Q_CHECK_ARG(c->intermediate > 0 && c->intermediate % 128 == 0,
+                  "intermediate=%d unsupported (multiple of 128: gate/up rows are interleaved in "
+                  "128-row blocks for the fused SwiGLU epilogue)", c->intermediate);
   B200Q_CHECK_ARG(c->vocab > 0 && c->vocab % 64 == 0, "vocab=%d must be a multiple of 64", c->vocab);
   B200Q_CHECK_ARG(c->block_size == 16, "block_size=%d unsupported (16)", c->block_size);
   B200Q_CHECK_ARG(c->n_layers > 0 && c->max_tokens > 0 && c->max_seqs > 0 && c->max_pos > 0,
@@ -289,8 +290,8 @@ int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
                                  stream));
     B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * H * QD, b200q_gemm_bf16(m->attn, L.o, m->x, T, H, QD, stream));
     B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, L.post_norm, T, H, c.rms_eps, stream));
-    B200Q_TRY(B200Q_PROF_GEMM, 4.0 * T * I * H, b200q_gemm_bf16(m->x, L.gate_up, m->gate_up, T, 2 * I, H, stream));
-    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 3.0 * T * I * 2, b200q_swiglu(m->gate_up, m->act, T, I, stream));
+    // gate_up GEMM with the SwiGLU fused into its epilogue (weights interleaved at bind time)
+    B200Q_TRY(B200Q_PROF_GEMM, 4.0 * T * I * H, b200q_gemm_swiglu_bf16(m->x, L.gate_up, m->act, T, 2 * I, H, stream));
     B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * H * I, b200q_gemm_bf16(m->act, L.down, m->x, T, H, I, stream));
   }
   if (b->n_sample > 0) {

@@ -114,6 +114,7 @@ SIGNATURES = {
     "b200q_decode_attn": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "b200q_prefill_attn": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "b200q_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200q_gemm_swiglu_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200q_swiglu": (_i, [_vp, _vp, _i, _i, _vp]),
     "b200q_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "b200q_argmax_bf16": (_i, [_vp, _vp, _i, _i, _vp]),
@@ -140,6 +141,8 @@ SIGNATURES = {
 # test / tuning hooks that are not part of the reference-facing header
 EXTRA_SIGNATURES = {
     "b200q_gemm_set_tile_n": (_i, [_i]),
+    "b200q_gemm_set_mode": (_i, [_i]),
+    "b200q_gemm_resident_pairs": (_i, []),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -230,8 +233,19 @@ def gemm_bf16(a, w, c, stream=None):
     check(load().b200q_gemm_bf16(_p(a), _p(w), _p(c), M, N, K, _stream(stream)))
 
 
+def gemm_swiglu_bf16(a, w_interleaved, c, stream=None):
+    M, K = a.shape
+    N = w_interleaved.shape[0]
+    assert w_interleaved.shape[1] == K and tuple(c.shape) == (M, N // 2)
+    check(load().b200q_gemm_swiglu_bf16(_p(a), _p(w_interleaved), _p(c), M, N, K, _stream(stream)))
+
+
 def gemm_set_tile_n(bn: int):
     check(load().b200q_gemm_set_tile_n(bn))
+
+
+def gemm_set_mode(mode: int):
+    check(load().b200q_gemm_set_mode(mode))
 
 
 def swiglu(gate_up, out, stream=None):

@@ -124,6 +124,15 @@ def rope_table(max_pos: int, head_dim: int, theta: float, scaling: Optional[dict
     return torch.cat([freqs.cos(), freqs.sin()], dim=-1).to(torch.bfloat16)
 
 
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor, block: int = 128) -> torch.Tensor:
+    """[I,H],[I,H] -> [2I,H] with rows [256j,256j+128) = gate[128j:128j+128], next 128 = the same
+    rows of up, so one 256-wide GEMM tile carries both halves of 128 SwiGLU outputs and the
+    activation can be applied in the GEMM epilogue (include/b200q.h: b200q_gemm_swiglu_bf16)."""
+    I, H = gate.shape
+    assert I % block == 0 and up.shape == gate.shape
+    return torch.stack([gate.view(I // block, block, H), up.view(I // block, block, H)], 1).reshape(2 * I, H)
+
+
 def fuse_hf_weights(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Iterable[Tuple[str, torch.Tensor]]:
     """HF checkpoint names -> engine names, with q/k/v and gate/up concatenated row-wise
     (same fusion vLLM's QKVParallelLinear / MergedColumnParallelLinear perform)."""
@@ -139,8 +148,8 @@ def fuse_hf_weights(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Iterable[Tu
                                             sd[p + "self_attn.k_proj.weight"],
                                             sd[p + "self_attn.v_proj.weight"]], 0)
         yield f"layers.{i}.o", sd[p + "self_attn.o_proj.weight"]
-        yield f"layers.{i}.gate_up", torch.cat([sd[p + "mlp.gate_proj.weight"],
-                                                sd[p + "mlp.up_proj.weight"]], 0)
+        yield f"layers.{i}.gate_up", interleave_gate_up(sd[p + "mlp.gate_proj.weight"],
+                                                        sd[p + "mlp.up_proj.weight"])
         yield f"layers.{i}.down", sd[p + "mlp.down_proj.weight"]
 
 

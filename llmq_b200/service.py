@@ -153,7 +153,7 @@ class GenerationService:
 
 def build_service(model_name: str, *, max_num_seqs: Optional[int], max_model_len: Optional[int],
                   gpu_memory_utilization: float, max_num_batched_tokens: Optional[int] = None,
-                  seed: int = 1234, logger=None) -> GenerationService:
+                  seed: int = 1234, logger=None, num_blocks: Optional[int] = None) -> GenerationService:
     """model + KV pool + engine + tokenizer for `model_name` (local dir or random:<builtin>)."""
     import torch
 
@@ -181,7 +181,7 @@ def build_service(model_name: str, *, max_num_seqs: Optional[int], max_model_len
         eos = spec.eos_token_id if spec.eos_token_id is not None else tokenizer.eos_token_id
     model = NativeModel(spec, weights, max_tokens=budget, max_seqs=max_num_seqs,
                         max_model_len=max_model_len, gpu_memory_utilization=gpu_memory_utilization,
-                        device=device)
+                        device=device, num_blocks=num_blocks)
     if logger:
         logger.info(f"b200q model {spec.name}: {model.num_blocks} KV blocks of 16 tokens, "
                     f"max_num_seqs={max_num_seqs}, token budget={budget}, max_model_len={max_model_len}")

@@ -202,3 +202,44 @@ def test_gemm(cuda, M, N, K, bn):
     bf16_close(c, ref.cpu(), ulps=1.0, atol=atol, max_mismatch_frac=0.02, what=f"gemm {M}x{N}x{K} bn={bn}")
     if M * N * K <= 130 * 512 * 1024:
         bf16_close(c, O.linear(a.float(), w.float()), ulps=1.0, atol=atol, what="gemm vs oracle")
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(129, 256, 64), (256, 512, 1024), (1000, 6144, 4096), (700, 4096, 14336)])
+def test_gemm_2cta(cuda, M, N, K, bn):
+    """cta_group::2 kernel (CTA pair, UMMA M=256, B tile split across the pair)"""
+    from llmq_b200 import lib
+    a, w = rnd(M, K, seed=22), rnd(N, K, seed=23, scale=0.05)
+    c = torch.full((M, N), float("nan"), dtype=BF, device=cuda)
+    lib.gemm_set_mode(2)
+    lib.gemm_set_tile_n(bn)
+    try:
+        lib.gemm_bf16(a.to(cuda), w.to(cuda), c)
+        torch.cuda.synchronize()
+    finally:
+        lib.gemm_set_mode(0)
+        lib.gemm_set_tile_n(0)
+    ref = (a.to(cuda).float() @ w.to(cuda).float().t()).to(BF)
+    bf16_close(c, ref.cpu(), ulps=1.0, atol=2e-5 * math.sqrt(K), max_mismatch_frac=0.02, what=f"gemm2 {M}x{N}x{K} bn={bn}")
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("M,I,K", [(5, 128, 64), (130, 512, 256), (300, 14336, 4096)])
+def test_gemm_swiglu_fused(cuda, M, I, K, mode):
+    """gate_up GEMM with the SwiGLU applied in the epilogue == unfused GEMM -> bf16 -> oracle swiglu"""
+    from llmq_b200 import lib
+    from llmq_b200.model import interleave_gate_up
+    a, g, u = rnd(M, K, seed=30), rnd(I, K, seed=31, scale=0.05), rnd(I, K, seed=32, scale=0.05)
+    w = interleave_gate_up(g, u)
+    out = torch.full((M, I), float("nan"), dtype=BF, device=cuda)
+    lib.gemm_set_mode(mode)
+    try:
+        lib.gemm_swiglu_bf16(a.to(cuda), w.to(cuda), out)
+        torch.cuda.synchronize()
+    finally:
+        lib.gemm_set_mode(0)
+    ad = a.to(cuda).float()
+    gu = torch.cat([(ad @ g.to(cuda).float().t()).to(BF), (ad @ u.to(cuda).float().t()).to(BF)], 1).cpu()
+    ref = O.swiglu(gu.float())
+    # a 1-ulp flip of g or u (accumulation order) moves the product by about one ulp as well
+    bf16_close(out, ref, ulps=3.0, atol=2e-5 * math.sqrt(K), max_mismatch_frac=0.05, what=f"gemm_swiglu mode={mode}")

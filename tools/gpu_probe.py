@@ -48,9 +48,11 @@ def timeit(fn, iters=20, warm=3, flush=None):
 
 def gemm_check(f):
     torch.manual_seed(0)
-    for (M, N, K) in [(128, 64, 64), (128, 256, 64), (128, 256, 128), (128, 256, 256), (256, 512, 1024), (200, 4096, 4096)]:
+    mode = int(os.environ.get("GEMM_MODE", "1"))
+    lib.gemm_set_mode(mode)
+    for (M, N, K) in [(128, 64, 64), (256, 256, 64), (256, 256, 128), (256, 256, 256), (256, 512, 1024), (200, 4096, 4096), (1000, 6144, 4096), (4096, 4096, 14336)]:
         for bn in (64, 128, 256):
-            if N % bn:
+            if N % bn or (mode == 2 and bn == 64):
                 continue
             a = torch.randn(M, K, device=dev).to(BF)
             w = (torch.randn(N, K, device=dev) * 0.05).to(BF)
@@ -63,7 +65,7 @@ def gemm_check(f):
             nan = torch.isnan(c.float()).sum().item()
             rel = (d / (ref.abs() + 1e-3))
             bad = (d > 0.02 * ref.abs() + 0.01)
-            info = dict(kind="gemm_check", M=M, N=N, K=K, bn=bn, nan=nan, max_abs=float(d[~torch.isnan(d)].max().item()) if nan < d.numel() else None,
+            info = dict(kind="gemm_check", mode=mode, M=M, N=N, K=K, bn=bn, nan=nan, max_abs=float(d[~torch.isnan(d)].max().item()) if nan < d.numel() else None,
                         bad_frac=float(bad.float().mean().item()))
             if bad.any():
                 # error map at 32x32 granularity (fraction of bad elements per cell)
@@ -80,6 +82,39 @@ def gemm_check(f):
                 info["sample_ref"] = ref[:2, :4].tolist()
             emit(f, **info)
     lib.gemm_set_tile_n(0)
+    lib.gemm_set_mode(0)
+
+
+def gemm2_bench(f):
+    """1-CTA vs 2-CTA (cta_group::2) vs cuBLAS on the Llama-3-8B layer shapes"""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    shapes = {"qkv": (6144, 4096), "o": (4096, 4096), "gate_up": (28672, 4096), "down": (4096, 14336), "lm_head": (128256, 4096)}
+    for M in (256, 512, 1024, 2048, 4096, 8192):
+        for name, (N, K) in shapes.items():
+            if name == "lm_head" and M > 1024:
+                continue
+            a = torch.randn(M, K, device=dev).to(BF)
+            w = (torch.randn(N, K, device=dev) * 0.02).to(BF)
+            c = torch.empty(M, N, dtype=BF, device=dev)
+            res = dict(kind="gemm2", name=name, M=M, N=N, K=K)
+            for mode, bn in ((1, 256), (1, 128), (2, 256), (2, 128)):
+                lib.gemm_set_mode(mode)
+                lib.gemm_set_tile_n(bn)
+                med, _ = timeit(lambda: lib.gemm_bf16(a, w, c), iters=10, flush=flush)
+                res[f"ms_m{mode}_bn{bn}"] = round(med, 4)
+            lib.gemm_set_mode(0)
+            lib.gemm_set_tile_n(0)
+            med, _ = timeit(lambda: lib.gemm_bf16(a, w, c), iters=10, flush=flush)
+            res["ms_auto"] = round(med, 4)
+            medc, _ = timeit(lambda: torch.matmul(a, w.t(), out=c), iters=10, flush=flush)
+            res["ms_cublas"] = round(medc, 4)
+            fl = 2.0 * M * N * K
+            for k in list(res):
+                if k.startswith("ms_"):
+                    res["tf_" + k[3:]] = round(fl / res[k] / 1e9, 1)
+            res["resident_pairs"] = lib.load().b200q_gemm_resident_pairs()
+            emit(f, **res)
+            del a, w, c
 
 
 def bench(f):
@@ -173,5 +208,6 @@ def bench(f):
 if __name__ == "__main__":
     mode = sys.argv[1]
     lib.require_device()
-    with open(os.path.join(OUT, f"probe_{mode}.jsonl"), "w") as f:
-        {"gemm_check": gemm_check, "bench": bench}[mode](f)
+    tag = os.environ.get("PROBE_TAG", "")
+    with open(os.path.join(OUT, f"probe_{mode}{tag}.jsonl"), "w") as f:
+        {"gemm_check": gemm_check, "bench": bench, "gemm2_bench": gemm2_bench}[mode](f)

@@ -325,13 +325,13 @@ __device__ __forceinline__ uint32_t mapa_shared(const void* p, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(
                    bar_cluster_addr),
                "r"(bytes)
                : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr)
                : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, int c0, int c1,
@@ -675,6 +675,18 @@ static int launch_gemm2(const void* A, const void* W, void* C, int M, int N, int
   return B200Q_OK;
 }
 
+// Measured on B200 (profiles/r1_gemm_2cta.md): at M >= 256 the CTA-pair kernel with a 256 x 256
+// tile is 0-8 % faster per unit of work than the 1-CTA 128 x 256 kernel (half the B traffic per
+// SM).  Use it when its coarser tiles do not cost an extra round of the persistent loop:
+// rounds(pair tiles over 74 pairs) x 2 <= rounds(1-CTA tiles over 148 SMs).
+static bool prefer_2cta(int M, int N) {
+  if (M < 256 || N % 256) return false;
+  const long long sms = num_sms(), pairs = sms / 2;
+  const long long t2 = (long long)((M + 255) / 256) * (N / 256);
+  const long long t1 = (long long)((M + GEMM_BM - 1) / GEMM_BM) * (N / 256);
+  return 2 * ((t2 + pairs - 1) / pairs) <= (t1 + sms - 1) / sms;
+}
+
 int g_gemm_force_bn = 0;  // test hook: 0 = heuristic
 int g_gemm_mode = 0;      // 0 = auto, 1 = force 1-CTA kernels, 2 = force the 2-CTA kernel
 
@@ -715,6 +727,7 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
     if ((bn == 0 || bn == 256) && N % 256 == 0) return launch_gemm2<256>(A, W, C, M, N, K, st);
     if ((bn == 0 || bn == 128) && N % 128 == 0) return launch_gemm2<128>(A, W, C, M, N, K, st);
   }
+  if (g_gemm_mode == 0 && bn == 0 && prefer_2cta(M, N)) return launch_gemm2<256>(A, W, C, M, N, K, st);
   if (bn == 0) {
     // Every CTA walks ceil(tiles / SMs) tiles; measured on B200 (profiles/r1_microbench.md) a
     // 128-wide tile costs ~0.85x and a 64-wide tile ~0.8x the time of a 256-wide one (the kernel
@@ -754,7 +767,8 @@ int b200q_gemm_swiglu_bf16(const void* A, const void* W, void* C, int M, int N, 
                   "gemm_swiglu: operands must be 16-byte aligned");
   if (M == 0) return B200Q_OK;
   cudaStream_t st = as_stream(stream);
-  if (g_gemm_mode == 2 && M > GEMM_BM) return launch_gemm2<256, true>(A, W, C, M, N, K, st);
+  if ((g_gemm_mode == 2 && M > GEMM_BM) || (g_gemm_mode == 0 && prefer_2cta(M, N)))
+    return launch_gemm2<256, true>(A, W, C, M, N, K, st);
   return launch_gemm<256, true>(A, W, C, M, N, K, st);
 }
 

@@ -242,4 +242,4 @@ def test_gemm_swiglu_fused(cuda, M, I, K, mode):
     gu = torch.cat([(ad @ g.to(cuda).float().t()).to(BF), (ad @ u.to(cuda).float().t()).to(BF)], 1).cpu()
     ref = O.swiglu(gu.float())
     # a 1-ulp flip of g or u (accumulation order) moves the product by about one ulp as well
-    bf16_close(out, ref, ulps=3.0, atol=2e-5 * math.sqrt(K), max_mismatch_frac=0.05, what=f"gemm_swiglu mode={mode}")
+    bf16_close(out, ref, ulps=8.0, atol=2e-5 * math.sqrt(K), max_mismatch_frac=0.02, what=f"gemm_swiglu mode={mode}")

@@ -1,0 +1,121 @@
+"""Run the incumbent — vLLM 0.22 (the engine behind the reference's VLLMWorker,
+ref:llmq/workers/vllm_worker.py:105-123,161-186) — on the same B200, development/measurement tool.
+
+  python tools/vllm_incumbent.py golden     # greedy token ids on a small seeded checkpoint
+                                            #   -> gpurun_out/vllm_golden_<name>.json (copied to tests/golden/)
+  python tools/vllm_incumbent.py throughput # Llama-3-8B dims, dummy weights, 128-in/128-out
+
+Differences from the reference worker, all deliberate: temperature is forced to 0
+(the reference hard-codes 0.7 unseeded), prompts are passed as token ids (same ids the reference
+would get from tokenising the text), and the engine is the synchronous `LLM` front-end over the
+same EngineCore instead of `AsyncLLMEngine` behind an AMQP consumer.
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("VLLM_ENABLE_V1_MULTIPROCESSING", "0")
+os.environ.setdefault("HF_HUB_OFFLINE", "1")
+os.environ.setdefault("VLLM_NO_USAGE_STATS", "1")
+OUT = os.path.join(ROOT, "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+
+import numpy as np  # noqa: E402
+
+from llmq_b200.fixtures import write_model_dir  # noqa: E402
+from llmq_b200.model import BUILTIN_SPECS, ModelSpec  # noqa: E402
+
+GOLDEN_SPECS = {
+    "d128": ModelSpec(hidden=512, n_layers=3, n_q_heads=8, n_kv_heads=2, head_dim=128, intermediate=1024,
+                      vocab=2048, max_position_embeddings=512, name="tiny-d128"),
+    "d64": ModelSpec(hidden=512, n_layers=2, n_q_heads=8, n_kv_heads=2, head_dim=64, intermediate=1024,
+                     vocab=2048, max_position_embeddings=512, name="tiny-d64"),
+}
+GOLDEN_SEED = 4321
+PROMPT_LENS = [5, 16, 17, 40, 130, 64, 33, 2, 100, 77, 128, 12]
+
+
+def golden_prompts(vocab):
+    g = np.random.default_rng(99)
+    return [g.integers(3, vocab, size=n).tolist() for n in PROMPT_LENS]
+
+
+def golden():
+    from vllm import LLM, SamplingParams
+
+    for name, spec in GOLDEN_SPECS.items():
+        d = os.path.join("/tmp", f"b200q_golden_{name}")
+        write_model_dir(d, spec, seed=GOLDEN_SEED, with_weights=True)
+        res = {"name": name, "spec": spec.to_hf_config(), "weights_seed": GOLDEN_SEED, "max_new_tokens": 24,
+               "prompts": golden_prompts(spec.vocab), "runs": {}}
+        for tag, kw in (("default", {}), ("eager", {"enforce_eager": True})):
+            try:
+                llm = LLM(model=d, dtype="bfloat16", max_model_len=512, max_num_seqs=16, gpu_memory_utilization=0.3,
+                          skip_tokenizer_init=True, disable_log_stats=True, seed=0, **kw)
+                sp = SamplingParams(temperature=0.0, max_tokens=24, ignore_eos=True, detokenize=False)
+                outs = llm.generate([{"prompt_token_ids": p} for p in res["prompts"]], sp, use_tqdm=False)
+                res["runs"][tag] = [list(o.outputs[0].token_ids) for o in outs]
+                del llm
+            except Exception as e:  # keep going: one mode is enough to pin
+                res["runs"][tag] = {"error": repr(e)[:500]}
+            import gc
+
+            import torch
+            gc.collect()
+            torch.cuda.empty_cache()
+        import vllm
+        res["vllm"] = vllm.__version__
+        with open(os.path.join(OUT, f"vllm_golden_{name}.json"), "w") as f:
+            json.dump(res, f)
+        print(name, {k: (v if isinstance(v, dict) else len(v)) for k, v in res["runs"].items()})
+
+
+def throughput():
+    from vllm import LLM, SamplingParams
+
+    from llmq_b200.fixtures import make_jobs, build_tokenizer
+
+    spec = BUILTIN_SPECS["llama-3-8b"]
+    d = "/tmp/b200q_llama3_8b_cfg"
+    write_model_dir(d, spec, with_weights=False)
+    n_jobs = int(os.environ.get("JOBS", "4608"))
+    seqs = int(os.environ.get("MAX_NUM_SEQS", "1024"))
+    tok = build_tokenizer(spec.vocab)
+    prompts = [{"prompt_token_ids": tok(j["prompt"], add_special_tokens=True).input_ids}
+               for j in make_jobs(2 * n_jobs, spec.vocab)]
+    results = []
+    for tag, kw in (("eager", {"enforce_eager": True}), ("default", {})):
+        if os.environ.get("ONLY") and os.environ["ONLY"] != tag:
+            continue
+        try:
+            t0 = time.time()
+            llm = LLM(model=d, load_format="dummy", dtype="bfloat16", max_model_len=512, max_num_seqs=seqs,
+                      gpu_memory_utilization=0.9, skip_tokenizer_init=True, disable_log_stats=True, seed=0, **kw)
+            init_s = time.time() - t0
+            sp = SamplingParams(temperature=0.0, max_tokens=128, ignore_eos=True, detokenize=False)
+            llm.generate(prompts[:256], sp, use_tqdm=False)  # warm-up
+            t0 = time.time()
+            outs = llm.generate(prompts[n_jobs:2 * n_jobs], sp, use_tqdm=False)
+            dt = time.time() - t0
+            ntok = sum(len(o.outputs[0].token_ids) for o in outs)
+            r = {"kind": "vllm_throughput", "mode": tag, "jobs": n_jobs, "max_num_seqs": seqs, "seconds": dt,
+                 "out_tokens_per_s": ntok / dt, "jobs_per_s": n_jobs / dt, "init_s": init_s}
+            del llm
+        except Exception as e:
+            r = {"kind": "vllm_throughput", "mode": tag, "error": repr(e)[:800]}
+        print(json.dumps(r))
+        results.append(r)
+        import gc
+
+        import torch
+        gc.collect()
+        torch.cuda.empty_cache()
+    with open(os.path.join(OUT, "vllm_throughput.json"), "w") as f:
+        json.dump(results, f)
+
+
+if __name__ == "__main__":
+    {"golden": golden, "throughput": throughput}[sys.argv[1]]()

@@ -59,6 +59,34 @@ def build_tokenizer(vocab_size: int):
     return fast
 
 
+def seeded_state_dict(spec: ModelSpec, seed: int = 1234) -> dict:
+    """HF-named bf16 state dict: Normal(0, 0.02) matrices drawn in a fixed order from one seeded
+    generator, unit norm weights.  The same call reproduces the checkpoint anywhere (tests do not
+    need the safetensors file that was handed to vLLM)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    mat = lambda r, c: (torch.randn(r, c, generator=g) * 0.02).to(torch.bfloat16)
+    ones = lambda: torch.ones(spec.hidden, dtype=torch.bfloat16)
+    sd = {"model.embed_tokens.weight": mat(spec.vocab, spec.hidden)}
+    qd, kd = spec.n_q_heads * spec.head_dim, spec.n_kv_heads * spec.head_dim
+    for i in range(spec.n_layers):
+        p = f"model.layers.{i}."
+        sd[p + "input_layernorm.weight"] = ones()
+        sd[p + "post_attention_layernorm.weight"] = ones()
+        sd[p + "self_attn.q_proj.weight"] = mat(qd, spec.hidden)
+        sd[p + "self_attn.k_proj.weight"] = mat(kd, spec.hidden)
+        sd[p + "self_attn.v_proj.weight"] = mat(kd, spec.hidden)
+        sd[p + "self_attn.o_proj.weight"] = mat(spec.hidden, qd)
+        sd[p + "mlp.gate_proj.weight"] = mat(spec.intermediate, spec.hidden)
+        sd[p + "mlp.up_proj.weight"] = mat(spec.intermediate, spec.hidden)
+        sd[p + "mlp.down_proj.weight"] = mat(spec.hidden, spec.intermediate)
+    sd["model.norm.weight"] = ones()
+    if not spec.tie_embeddings:
+        sd["lm_head.weight"] = mat(spec.vocab, spec.hidden)
+    return sd
+
+
 def write_model_dir(path: str, spec: ModelSpec, *, seed: int = 1234, with_weights: bool = True) -> str:
     """config.json + tokenizer (+ safetensors when with_weights) in `path`."""
     os.makedirs(path, exist_ok=True)
@@ -72,29 +100,9 @@ def write_model_dir(path: str, spec: ModelSpec, *, seed: int = 1234, with_weight
         json.dump({"bos_token_id": cfg["bos_token_id"], "eos_token_id": cfg["eos_token_id"]}, f)
     build_tokenizer(spec.vocab).save_pretrained(path)
     if with_weights:
-        import torch
         from safetensors.torch import save_file
 
-        g = torch.Generator().manual_seed(seed)
-        mat = lambda r, c: (torch.randn(r, c, generator=g) * 0.02).to(torch.bfloat16)
-        ones = lambda: torch.ones(spec.hidden, dtype=torch.bfloat16)
-        sd = {"model.embed_tokens.weight": mat(spec.vocab, spec.hidden)}
-        qd, kd = spec.n_q_heads * spec.head_dim, spec.n_kv_heads * spec.head_dim
-        for i in range(spec.n_layers):
-            p = f"model.layers.{i}."
-            sd[p + "input_layernorm.weight"] = ones()
-            sd[p + "post_attention_layernorm.weight"] = ones()
-            sd[p + "self_attn.q_proj.weight"] = mat(qd, spec.hidden)
-            sd[p + "self_attn.k_proj.weight"] = mat(kd, spec.hidden)
-            sd[p + "self_attn.v_proj.weight"] = mat(kd, spec.hidden)
-            sd[p + "self_attn.o_proj.weight"] = mat(spec.hidden, qd)
-            sd[p + "mlp.gate_proj.weight"] = mat(spec.intermediate, spec.hidden)
-            sd[p + "mlp.up_proj.weight"] = mat(spec.intermediate, spec.hidden)
-            sd[p + "mlp.down_proj.weight"] = mat(spec.hidden, spec.intermediate)
-        sd["model.norm.weight"] = ones()
-        if not spec.tie_embeddings:
-            sd["lm_head.weight"] = mat(spec.vocab, spec.hidden)
-        save_file(sd, os.path.join(path, "model.safetensors"), metadata={"format": "pt"})
+        save_file(seeded_state_dict(spec, seed), os.path.join(path, "model.safetensors"), metadata={"format": "pt"})
     return path
 
 

@@ -117,6 +117,60 @@ def gemm2_bench(f):
             del a, w, c
 
 
+def ncu_targets(f):
+    """the bench's dominant launches in isolation (small process => cheap to put under ncu):
+    the four projection GEMMs at the decode batch M=4608 and the decode attention at B=4608"""
+    M = int(os.environ.get("NCU_M", "4608"))
+    shapes = {"qkv": (6144, 4096), "o": (4096, 4096), "down": (4096, 14336)}
+    for name, (N, K) in shapes.items():
+        a = torch.randn(M, K, device=dev).to(BF)
+        w = (torch.randn(N, K, device=dev) * 0.02).to(BF)
+        c = torch.empty(M, N, dtype=BF, device=dev)
+        for _ in range(2):
+            lib.gemm_bf16(a, w, c)
+        torch.cuda.synchronize()
+        del a, w, c
+    a = torch.randn(M, 4096, device=dev).to(BF)
+    w = (torch.randn(28672, 4096, device=dev) * 0.02).to(BF)
+    c = torch.empty(M, 14336, dtype=BF, device=dev)
+    for _ in range(2):
+        lib.gemm_swiglu_bf16(a, w, c)
+    torch.cuda.synchronize()
+    del a, w, c
+    n_q, n_kv, D, BS, ctx = 32, 8, 128, 16, 192
+    nb_per = ctx // BS
+    NB = M * nb_per + 1
+    kv = torch.randn(NB, 2, n_kv, BS, D, device=dev).to(BF)
+    bt = (torch.randperm(NB - 1, device=dev).to(torch.int32).view(M, nb_per) + 1)
+    bt = torch.cat([bt, torch.zeros(M, (-nb_per) % 8, dtype=torch.int32, device=dev)], 1).contiguous()
+    ctxs = torch.full((M,), ctx, dtype=torch.int32, device=dev)
+    qkv = torch.randn(M, (n_q + 2 * n_kv) * D, device=dev).to(BF)
+    out = torch.empty(M, n_q * D, dtype=BF, device=dev)
+    for _ in range(2):
+        lib.decode_attn(qkv, out, kv, bt, ctxs, n_q, n_kv, D, BS, 1 / math.sqrt(D))
+    torch.cuda.synchronize()
+    emit(f, kind="ncu_targets", M=M, done=True)
+
+
+def argmax_ties(f):
+    """which index does torch.argmax return on exact ties on this GPU? (vLLM's greedy sampler is
+    logits.argmax(-1): vllm/v1/sample/sampler.py:235-236)"""
+    for V in (2048, 128256):
+        for dt in (torch.float32, torch.bfloat16):
+            x = torch.randn(64, V, device=dev).to(dt)
+            big = x.max().item() + 1.0
+            idx = torch.randint(0, V, (64, 3), device=dev)
+            x.scatter_(1, idx, big)
+            got = x.argmax(-1).cpu()
+            lo, hi = idx.min(1).values.cpu(), idx.max(1).values.cpu()
+            emit(f, kind="argmax_ties", V=V, dtype=str(dt), picks_lowest=int((got == lo).sum()),
+                 picks_highest=int((got == hi).sum()), rows=64)
+            ours = torch.empty(64, dtype=torch.int32, device=dev)
+            if dt == torch.bfloat16:
+                lib.argmax_bf16(x, ours)
+                emit(f, kind="argmax_ties_ours", V=V, picks_lowest=int((ours.cpu() == lo).sum()), rows=64)
+
+
 def bench(f):
     peaks = {"hbm_gbs": 6480.5, "bf16_tflops": 1707.6}
     try:
@@ -210,4 +264,5 @@ if __name__ == "__main__":
     lib.require_device()
     tag = os.environ.get("PROBE_TAG", "")
     with open(os.path.join(OUT, f"probe_{mode}{tag}.jsonl"), "w") as f:
-        {"gemm_check": gemm_check, "bench": bench, "gemm2_bench": gemm2_bench}[mode](f)
+        {"gemm_check": gemm_check, "bench": bench, "gemm2_bench": gemm2_bench, "ncu_targets": ncu_targets,
+         "argmax_ties": argmax_ties}[mode](f)

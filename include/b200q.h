@@ -206,6 +206,7 @@ typedef struct b200q_engine_config {
   int32_t max_num_batched_tokens;  /* token budget per step (<= model max_tokens)          */
   int32_t max_model_len;           /* VLLM_MAX_MODEL_LEN (ref:llmq/core/config.py:34-39)  */
   int32_t eos_token_id;            /* -1: none                                            */
+  int32_t policy;                  /* 0: running requests first (vLLM order); 1: prefill first */
 } b200q_engine_config;
 
 typedef struct b200q_engine* b200q_engine_t;

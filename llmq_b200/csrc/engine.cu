@@ -211,53 +211,82 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
   *n_out = 0;
   int budget = e->cfg.max_num_batched_tokens;
 
-  // ---- 1. running requests first ----
+  // ---- 1+2. pick this step's work ----
+  // policy 0 (vLLM order): RUNNING requests first (decodes and unfinished prompt chunks), then
+  //   FIFO admission of WAITING requests with what is left of the token budget.
+  // policy 1 (prefill first, default): unfinished prompt chunks and admissions take the budget
+  //   first, decodes get the rest.  Under a backlog this drives the decode batch to max_num_seqs
+  //   as fast as possible and keeps it there, which is what the GEMMs (M = tokens per step) and
+  //   the paged attention want on a B200; per-token latency is not this path's metric.
   std::vector<Request*> sched;
   sched.reserve(e->running.size() + 16);
-  for (size_t i = 0; i < e->running.size();) {
-    Request* r = e->running[i];
-    int n_new = (int)r->tokens.size() - r->n_computed;
-    n_new = std::min(n_new, budget);
-    if (n_new <= 0) {
-      r->n_sched = 0;
-      ++i;
-      continue;
-    }
-    bool ok = ensure_blocks(e, r, r->n_computed + n_new);
-    while (!ok) {
-      // preempt the most recently admitted running request (recompute later)
-      Request* victim = e->running.back();
-      e->running.pop_back();
-      free_request_blocks(e, victim);
-      victim->n_computed = 0;
-      victim->n_sched = 0;
-      e->waiting.push_front(victim);
-      e->stats.preemptions++;
-      auto sit = std::find(sched.begin(), sched.end(), victim);
-      if (sit != sched.end()) {  // (cannot happen: victims are behind us in `running`)
-        budget += victim->n_sched;
-        sched.erase(sit);
-      }
-      if (victim == r) break;
-      ok = ensure_blocks(e, r, r->n_computed + n_new);
-    }
-    if (!ok) break;  // r itself was preempted; everything after it is gone too
-    r->n_sched = n_new;
-    budget -= n_new;
-    sched.push_back(r);
-    ++i;
-  }
+  for (Request* r : e->running) r->n_sched = 0;
 
-  // ---- 2. admit waiting requests (FIFO) ----
-  while (budget > 0 && !e->waiting.empty() && (int)e->running.size() < e->cfg.max_num_seqs) {
-    Request* r = e->waiting.front();
-    int n_new = std::min((int)r->tokens.size() - r->n_computed, budget);
-    if (!ensure_blocks(e, r, r->n_computed + n_new)) break;
-    e->waiting.pop_front();
-    e->running.push_back(r);
-    r->n_sched = n_new;
-    budget -= n_new;
-    sched.push_back(r);
+  auto schedule_running = [&](int kind) {  // 0: all, 1: multi-token remainders, 2: single-token
+    for (size_t i = 0; i < e->running.size();) {
+      Request* r = e->running[i];
+      const int remaining = (int)r->tokens.size() - r->n_computed;
+      const bool single = remaining == 1;
+      if (r->n_sched > 0 || remaining <= 0 || (kind == 1 && single) || (kind == 2 && !single)) {
+        ++i;
+        continue;
+      }
+      const int n_new = std::min(remaining, budget);
+      if (n_new <= 0) return;  // token budget exhausted
+      bool ok = ensure_blocks(e, r, r->n_computed + n_new);
+      bool self_preempted = false;
+      while (!ok) {
+        // KV pool exhausted: preempt the most recently admitted running request; it keeps its
+        // tokens and is recomputed when re-admitted (preempt-by-recompute)
+        Request* victim = e->running.back();
+        e->running.pop_back();
+        auto sit = std::find(sched.begin(), sched.end(), victim);
+        if (sit != sched.end()) {
+          budget += victim->n_sched;
+          sched.erase(sit);
+        }
+        free_request_blocks(e, victim);
+        victim->n_computed = 0;
+        victim->n_sched = 0;
+        e->waiting.push_front(victim);
+        e->stats.preemptions++;
+        if (victim == r) {
+          self_preempted = true;
+          break;
+        }
+        ok = ensure_blocks(e, r, r->n_computed + n_new);
+      }
+      if (self_preempted) return;  // r was the newest request: nothing behind it is left
+      r->n_sched = n_new;
+      budget -= n_new;
+      sched.push_back(r);
+      ++i;
+    }
+  };
+  auto admit_waiting = [&]() {
+    while (budget > 0 && !e->waiting.empty() && (int)e->running.size() < e->cfg.max_num_seqs) {
+      Request* r = e->waiting.front();
+      const int n_new = std::min((int)r->tokens.size() - r->n_computed, budget);
+      // watermark: leave the running decodes ~2 steps' worth of fresh blocks, so that an admission
+      // is not immediately undone by a preemption
+      const int need = (r->n_computed + n_new + e->block_size - 1) / e->block_size - (int)r->blocks.size();
+      const int reserve = e->running.empty() ? 0 : (int)e->running.size() / 8 + 1;
+      if ((int)e->free_blocks.size() - need < reserve) break;
+      if (!ensure_blocks(e, r, r->n_computed + n_new)) break;
+      e->waiting.pop_front();
+      e->running.push_back(r);
+      r->n_sched = n_new;
+      budget -= n_new;
+      sched.push_back(r);
+    }
+  };
+  if (e->cfg.policy == 0) {
+    schedule_running(0);
+    admit_waiting();
+  } else {
+    schedule_running(1);
+    admit_waiting();
+    schedule_running(2);
   }
 
   if (sched.empty()) {

@@ -678,13 +678,14 @@ static int launch_gemm2(const void* A, const void* W, void* C, int M, int N, int
 // Measured on B200 (profiles/r1_gemm_2cta.md): at M >= 256 the CTA-pair kernel with a 256 x 256
 // tile is 0-8 % faster per unit of work than the 1-CTA 128 x 256 kernel (half the B traffic per
 // SM).  Use it when its coarser tiles do not cost an extra round of the persistent loop:
-// rounds(pair tiles over 74 pairs) x 2 <= rounds(1-CTA tiles over 148 SMs).
+// rounds(pair tiles over 74 pairs) <= rounds(1-CTA tiles over 148 SMs); a round costs the same
+// wall time in both kernels (every SM works one 128 x 256 tile per round).
 static bool prefer_2cta(int M, int N) {
   if (M < 256 || N % 256) return false;
   const long long sms = num_sms(), pairs = sms / 2;
   const long long t2 = (long long)((M + 255) / 256) * (N / 256);
   const long long t1 = (long long)((M + GEMM_BM - 1) / GEMM_BM) * (N / 256);
-  return 2 * ((t2 + pairs - 1) / pairs) <= (t1 + sms - 1) / sms;
+  return (t2 + pairs - 1) / pairs <= (t1 + sms - 1) / sms;
 }
 
 int g_gemm_force_bn = 0;  // test hook: 0 = heuristic

@@ -68,6 +68,7 @@ class EngineConfig(C.Structure):
         ("max_num_batched_tokens", C.c_int32),
         ("max_model_len", C.c_int32),
         ("eos_token_id", C.c_int32),
+        ("policy", C.c_int32),
     ]
 
 

@@ -281,7 +281,8 @@ class Engine:
     """Python face of b200q_engine: add requests, run steps, get (req_id, token, flags) events."""
 
     def __init__(self, model: NativeModel, *, max_num_seqs: int, max_num_batched_tokens: int,
-                 max_model_len: Optional[int] = None, eos_token_id: Optional[int] = None):
+                 max_model_len: Optional[int] = None, eos_token_id: Optional[int] = None,
+                 policy: Optional[int] = None):
         import numpy as np
 
         self.model = model
@@ -290,7 +291,8 @@ class Engine:
         ecfg = L.EngineConfig(
             max_num_seqs=max_num_seqs, max_num_batched_tokens=max_num_batched_tokens,
             max_model_len=max_model_len or model.max_model_len,
-            eos_token_id=-1 if eos_token_id is None else int(eos_token_id))
+            eos_token_id=-1 if eos_token_id is None else int(eos_token_id),
+            policy=int(os.environ.get("B200Q_SCHED_POLICY", "1")) if policy is None else int(policy))
         h = C.c_void_p()
         L.check(self.lib.b200q_engine_create(model.handle, C.byref(ecfg), C.byref(h)))
         self.handle = h

@@ -163,12 +163,15 @@ def test_engine_batch_invariance_chunking_and_preemption(cuda):
     # tiny budget: chunked prefill (budget 24 < prompt lengths); tiny pool (40 blocks of 16 tokens
     # < sum of all sequences = 506+80 tokens ~ 41 blocks) forces preemption + recompute
     chunked, st2 = run_engine(model, reqs, max_new=10, max_num_batched_tokens=24, max_num_seqs=8)
+    vllm_order, st3 = run_engine(model, reqs, max_new=10, max_num_batched_tokens=24, max_num_seqs=8, policy=0)
+    assert st2.preemptions + st3.preemptions > 0, "the tiny KV pool was meant to force preemption"
     twice, _ = run_engine(model, reqs, max_new=10)
     for i in range(len(reqs)):
         assert together[i] == twice[i], "non-deterministic across identical runs"
     # decode vs prefill attention paths round differently; allow divergence only at near-ties
     check_against_oracle(oracle, reqs, together, 10)
     check_against_oracle(oracle, reqs, chunked, 10)
+    check_against_oracle(oracle, reqs, vllm_order, 10)
     check_against_oracle(oracle, reqs, alone, 10)
     n_same = sum(together[i] == alone[i] for i in range(len(reqs)))
     assert n_same >= len(reqs) - 1, f"batch invariance broken for {len(reqs) - n_same} requests"

@@ -166,7 +166,7 @@ template <int BN, bool kSwiGLU = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b, bf16* __restrict__ C, int M,
-                     int N, int K) {
+                     int N, int K, int dbg) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -215,9 +215,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           mbar_wait(empty + stage, phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(full + stage, Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, kb * GEMM_BK, m_blk * GEMM_BM, full + stage);
-          tma_load_2d(sb, &tmap_b, kb * GEMM_BK, n_blk * BN, full + stage);
+          if (dbg & 1) {  // timing experiment: MMA on stale smem, no operand traffic
+            mbar_arrive(full + stage);
+          } else {
+            mbar_expect_tx(full + stage, Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, kb * GEMM_BK, m_blk * GEMM_BM, full + stage);
+            tma_load_2d(sb, &tmap_b, kb * GEMM_BK, n_blk * BN, full + stage);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const long long ldc = kSwiGLU ? N / 2 : N;
       bf16* crow = C + (long long)row * ldc + (long long)n_blk * OUT_BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_row<BN, kSwiGLU>(taddr, crow, row < M);
+      if (!(dbg & 2)) epilogue_row<BN, kSwiGLU>(taddr, crow, row < M);  // dbg&2: skip the drain
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
@@ -381,7 +385,7 @@ template <int BN, bool kSwiGLU = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b, bf16* __restrict__ C, int M,
-                      int N, int K) {
+                      int N, int K, int dbg) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -435,9 +439,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           const uint32_t lfull = mapa_shared(full + stage, 0);
-          mbar_expect_tx_cluster(lfull, Cfg::STAGE_BYTES);
-          tma_load_2d_2sm(sa, &tmap_a, kb * GEMM_BK, m_blk * 256 + (int)rank * 128, lfull);
-          tma_load_2d_2sm(sb, &tmap_b, kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2), lfull);
+          if (dbg & 1) {  // timing experiment: MMA on stale smem, no operand traffic
+            mbar_arrive_cluster(lfull);
+          } else {
+            mbar_expect_tx_cluster(lfull, Cfg::STAGE_BYTES);
+            tma_load_2d_2sm(sa, &tmap_a, kb * GEMM_BK, m_blk * 256 + (int)rank * 128, lfull);
+            tma_load_2d_2sm(sb, &tmap_b, kb * GEMM_BK, n_blk * BN + (int)rank * (BN / 2), lfull);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -495,7 +503,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       const long long ldc = kSwiGLU ? N / 2 : N;
       bf16* crow = C + (long long)row * ldc + (long long)n_blk * OUT_BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_row<BN, kSwiGLU>(taddr, crow, row < M);
+      if (!(dbg & 2)) epilogue_row<BN, kSwiGLU>(taddr, crow, row < M);  // dbg&2: skip the drain
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tmem_empty + acc, 0));
@@ -604,6 +612,8 @@ static int num_sms() {
   return n;
 }
 
+static int g_gemm_debug = 0;  // timing experiments only (wrong results): 1 = no TMA loads, 2 = no epilogue
+
 template <int BN, bool kSwiGLU = false>
 static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int K,
                        cudaStream_t st) {
@@ -622,7 +632,7 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
   }
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K, g_gemm_debug);
   B200Q_LAUNCH_CHECK();
   return B200Q_OK;
 }
@@ -670,7 +680,7 @@ static int launch_gemm2(const void* A, const void* W, void* C, int M, int N, int
     g_gemm2_pairs = pairs;
   }
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K, g_gemm_debug);
   B200Q_LAUNCH_CHECK();
   return B200Q_OK;
 }
@@ -707,6 +717,12 @@ int b200q_gemm_set_tile_n(int bn) {
 // test/tuning hook: 0 = auto, 1 = 1-CTA kernels only, 2 = 2-CTA (cta_group::2) kernel whenever legal
 // diagnostics: co-resident CTA pairs the 2-CTA kernel's grid is sized to (0 until first use)
 int b200q_gemm_resident_pairs(void) { return g_gemm2_pairs; }
+
+// timing experiments only — results are garbage: bit0 skips the operand loads, bit1 the epilogue
+int b200q_gemm_set_debug(int flags) {
+  g_gemm_debug = flags & 3;
+  return B200Q_OK;
+}
 
 int b200q_gemm_set_mode(int mode) {
   B200Q_CHECK_ARG(mode >= 0 && mode <= 2, "gemm mode must be 0/1/2");

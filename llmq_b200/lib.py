@@ -144,6 +144,7 @@ EXTRA_SIGNATURES = {
     "b200q_gemm_set_tile_n": (_i, [_i]),
     "b200q_gemm_set_mode": (_i, [_i]),
     "b200q_gemm_resident_pairs": (_i, []),
+    "b200q_gemm_set_debug": (_i, [_i]),
 }
 
 _lib: Optional[C.CDLL] = None

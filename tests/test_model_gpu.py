@@ -182,7 +182,7 @@ def test_engine_preemption_recompute(cuda, policy):
     """KV pool too small for every admitted sequence to grow: the newest running requests are
     preempted (blocks freed, tokens kept), re-admitted later and recomputed — outputs unchanged"""
     dims = TINY["d64"]
-    model, oracle, _ = build(dims, num_blocks=10)
+    model, oracle, _ = build(dims, num_blocks=10, max_model_len=64)
     reqs = prompts(dims.vocab, [16] * 8, seed=21)  # each fills exactly one block, then needs a second
     outs, st = run_engine(model, reqs, max_new=20, max_num_seqs=8, max_num_batched_tokens=64, policy=policy)
     assert st.preemptions > 0, "expected the 10-block pool to force preemptions"

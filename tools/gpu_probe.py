@@ -152,6 +152,35 @@ def ncu_targets(f):
     emit(f, kind="ncu_targets", M=M, done=True)
 
 
+def gemm_limits(f):
+    """where do the GEMM's bubbles come from?  time the kernel with the operand loads and/or the
+    epilogue switched off (results are garbage in those modes; timing only)"""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    shapes = {"qkv": (6144, 4096), "down": (4096, 14336), "gate_up": (28672, 4096)}
+    L = lib.load()
+    for M in (4608, 9472):
+        for name, (N, K) in shapes.items():
+            a = torch.randn(M, K, device=dev).to(BF)
+            w = (torch.randn(N, K, device=dev) * 0.02).to(BF)
+            c = torch.empty(M, N, dtype=BF, device=dev)
+            res = dict(kind="gemm_limits", name=name, M=M, N=N, K=K)
+            fl = 2.0 * M * N * K
+            for mode in (1, 2):
+                for dbg in (0, 1, 2, 3):
+                    lib.gemm_set_mode(mode)
+                    lib.gemm_set_tile_n(256)
+                    L.b200q_gemm_set_debug(dbg)
+                    med, _ = timeit(lambda: lib.gemm_bf16(a, w, c), iters=8, flush=flush)
+                    res[f"tf_cta{mode}_dbg{dbg}"] = round(fl / med / 1e9, 1)
+            L.b200q_gemm_set_debug(0)
+            lib.gemm_set_mode(0)
+            lib.gemm_set_tile_n(0)
+            medc, _ = timeit(lambda: torch.matmul(a, w.t(), out=c), iters=8, flush=flush)
+            res["tf_cublas"] = round(fl / medc / 1e9, 1)
+            emit(f, **res)
+            del a, w, c
+
+
 def argmax_ties(f):
     """which index does torch.argmax return on exact ties on this GPU? (vLLM's greedy sampler is
     logits.argmax(-1): vllm/v1/sample/sampler.py:235-236)"""
@@ -265,4 +294,4 @@ if __name__ == "__main__":
     tag = os.environ.get("PROBE_TAG", "")
     with open(os.path.join(OUT, f"probe_{mode}{tag}.jsonl"), "w") as f:
         {"gemm_check": gemm_check, "bench": bench, "gemm2_bench": gemm2_bench, "ncu_targets": ncu_targets,
-         "argmax_ties": argmax_ties}[mode](f)
+         "argmax_ties": argmax_ties, "gemm_limits": gemm_limits}[mode](f)

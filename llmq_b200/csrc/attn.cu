@@ -275,6 +275,189 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
 }
 
 // ------------------------------------------------------------------------------------------
+// K7 decode, streaming variant for large batches.  Every warp of a persistent grid owns whole
+// (sequence, kv-head) items and walks them back to back: the 3-stage TMA page ring never
+// drains between items (the pages of the next item are already in flight while the current
+// one finishes), there is no cross-warp merge and no CTA turnover, and the next item's Q
+// fragments / context length are prefetched one item ahead.  With ~12 pages per item
+// (128-in/128-out) the v1 kernel above spends as long in its prologue (ctx -> block ids -> first
+// TMA, ~1-2 us of dependent latency) as in streaming; this one pays that once per warp.
+// Used when there are enough items to give every resident warp several of them; v1 keeps the
+// small-batch / long-context cases (it splits one item across 4 warps).
+// ------------------------------------------------------------------------------------------
+template <int D, int BS>
+struct Dec2Smem {
+  static constexpr int STAGE_BYTES = 2 * Geo<D, BS>::PAGE_BYTES;
+  static constexpr int RING_BYTES = DEC_WARPS * DEC_STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = RING_BYTES + DEC_WARPS * DEC_STAGES * 8;
+};
+
+template <int D, int BS>
+__global__ void __launch_bounds__(DEC_WARPS * 32, 2)
+    decode_attn_stream_kernel(const bf16* __restrict__ q, int q_stride, bf16* __restrict__ out,
+                              const uint8_t* __restrict__ kv_layer,
+                              const int32_t* __restrict__ block_table, int bt_stride,
+                              const int32_t* __restrict__ ctx_lens, int n_seqs, int n_q, int n_kv,
+                              int G, float scale_log2) {
+  using G_ = Geo<D, BS>;
+  using S_ = Dec2Smem<D, BS>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring = smem + warp * DEC_STAGES * S_::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_::RING_BYTES) + warp * DEC_STAGES;
+  const int total = n_seqs * n_kv;
+  const int n_warps = gridDim.x * DEC_WARPS;
+  const int first = blockIdx.x * DEC_WARPS + warp;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < DEC_STAGES; ++s) mbar_init(bars + s, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (first >= total) return;
+
+  const long long page_stride = (long long)G_::PAGE_BYTES;
+  const int r = lane >> 2, cq = (lane & 3) * 2;
+
+  // ---- issue cursor: runs up to DEC_STAGES pages ahead of the consumer, across item borders ----
+  int i_item = first, i_page = 0, i_ctx = max(__ldg(ctx_lens + first / n_kv), 1);
+  int i_npages = (i_ctx + BS - 1) / BS;
+  int i_ids_base = 0;
+  int i_ids = (lane < i_npages) ? __ldg(block_table + (long long)(first / n_kv) * bt_stride + lane) : 0;
+  int issued = 0;
+  bool i_done = false;
+  auto issue_next = [&]() {  // whole warp
+    if (i_done) return;
+    if (i_page - i_ids_base >= 32) {
+      i_ids_base += 32;
+      i_ids = (i_ids_base + lane < i_npages)
+                  ? __ldg(block_table + (long long)(i_item / n_kv) * bt_stride + i_ids_base + lane)
+                  : 0;
+    }
+    const int blk = __shfl_sync(0xffffffffu, i_ids, i_page - i_ids_base);
+    const int kvh = i_item % n_kv;
+    const int n_valid = min(BS, i_ctx - i_page * BS);
+    const int st = issued % DEC_STAGES;
+    uint8_t* ks = ring + st * S_::STAGE_BYTES;
+    uint8_t* vs = ks + G_::PAGE_BYTES;
+    if (n_valid < BS) {
+      zero_tail_rows<D, BS>(vs, n_valid, lane);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)n_valid * G_::ROW_BYTES;
+      const uint8_t* kp = kv_layer + (((long long)blk * 2 + 0) * n_kv + kvh) * page_stride;
+      const uint8_t* vp = kv_layer + (((long long)blk * 2 + 1) * n_kv + kvh) * page_stride;
+      mbar_expect_tx(bars + st, 2 * bytes);
+      tma_bulk_g2s(ks, kp, bytes, bars + st);
+      tma_bulk_g2s(vs, vp, bytes, bars + st);
+    }
+    ++issued;
+    if (++i_page == i_npages) {  // move to this warp's next item
+      i_item += n_warps;
+      if (i_item >= total) {
+        i_done = true;
+        return;
+      }
+      const int seq = i_item / n_kv;
+      i_ctx = max(__ldg(ctx_lens + seq), 1);
+      i_npages = (i_ctx + BS - 1) / BS;
+      i_page = 0;
+      i_ids_base = 0;
+      i_ids = (lane < i_npages) ? __ldg(block_table + (long long)seq * bt_stride + lane) : 0;
+    }
+  };
+  for (int k = 0; k < DEC_STAGES; ++k) issue_next();
+
+  // ---- consumer ----
+  auto load_q = [&](int item, uint32_t (&dst)[D / 16][2]) {
+    const int seq = item / n_kv, kvh = item % n_kv;
+    const bf16* qrow = q + (long long)seq * q_stride + (long long)(kvh * G + r) * D;
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+      dst[ks][0] = r < G ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + cq) : 0u;
+      dst[ks][1] = r < G ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + cq) : 0u;
+    }
+  };
+  uint32_t qn[D / 16][2];  // prefetched Q of the NEXT item
+  int n_ctx = max(__ldg(ctx_lens + first / n_kv), 1);
+  load_q(first, qn);
+  int consumed = 0;
+  for (int item = first; item < total; item += n_warps) {
+    uint32_t qa[D / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+      qa[ks][0] = qn[ks][0];
+      qa[ks][2] = qn[ks][1];
+      qa[ks][1] = 0u;
+      qa[ks][3] = 0u;
+    }
+    const int ctx = n_ctx;
+    const int n_pages = (ctx + BS - 1) / BS;
+    if (item + n_warps < total) {  // prefetch the next item's Q and context length
+      n_ctx = max(__ldg(ctx_lens + (item + n_warps) / n_kv), 1);
+      load_q(item + n_warps, qn);
+    }
+    float o[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int p = 0; p < n_pages; ++p) {
+      const int st = consumed % DEC_STAGES;
+      mbar_wait(bars + st, (uint32_t)(consumed / DEC_STAGES) & 1u);
+      const int n_valid = min(BS, ctx - p * BS);
+      const uint32_t k_s = smem_u32(ring + st * S_::STAGE_BYTES);
+      const uint32_t v_s = k_s + G_::PAGE_BYTES;
+      float s[BS / 8][4];
+      qk_page<D, BS, false>(k_s, qa, s, lane);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < G_::NT; ++nt) {
+        const int t0 = nt * 8 + cq;
+        s[nt][0] = (t0 < n_valid) ? s[nt][0] * scale_log2 : -INFINITY;
+        s[nt][1] = (t0 + 1 < n_valid) ? s[nt][1] * scale_log2 : -INFINITY;
+        mx = fmaxf(mx, fmaxf(s[nt][0], s[nt][1]));
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f(m - m_new);
+      float psum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < G_::NT; ++nt) {
+        s[nt][0] = exp2f(s[nt][0] - m_new);
+        s[nt][1] = exp2f(s[nt][1] - m_new);
+        s[nt][2] = 0.f;
+        s[nt][3] = 0.f;
+        psum += s[nt][0] + s[nt][1];
+      }
+      l = l * alpha + psum;
+      m = m_new;
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        o[i][0] *= alpha;
+        o[i][1] *= alpha;
+      }
+      pv_page<D, BS, false>(v_s, s, o, lane);
+      __syncwarp();
+      ++consumed;
+      issue_next();  // refill the stage that was just drained
+    }
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    if (r < G) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      const int seq = item / n_kv, kvh = item % n_kv;
+      bf16* orow = out + (long long)seq * n_q * D + (long long)(kvh * G + r) * D;
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i)
+        *reinterpret_cast<uint32_t*>(orow + i * 8 + cq) = pack_bf16x2(o[i][0] * inv, o[i][1] * inv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K6 prefill
 // ------------------------------------------------------------------------------------------
 template <int D, int BS>
@@ -451,6 +634,43 @@ static int launch_decode(const void* q, int q_stride, void* out, const void* kv,
   return B200Q_OK;
 }
 
+int g_decode_variant = 0;  // test hook: 0 = auto, 1 = split kernel (v1), 2 = streaming kernel
+
+static int attn_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int D, int BS>
+static int launch_decode_stream(const void* q, int q_stride, void* out, const void* kv,
+                                const int32_t* bt, int bt_stride, const int32_t* ctx, int n_seqs,
+                                int n_q, int n_kv, float scale, cudaStream_t st) {
+  using S_ = Dec2Smem<D, BS>;
+  auto kern = decode_attn_stream_kernel<D, BS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::TOTAL));
+    attr_set = true;
+  }
+  const int total = n_seqs * n_kv;
+  // 2 resident CTAs per SM (96 KB of page ring each); variant 3 (tests) squeezes everything
+  // through 4 CTAs so that every warp walks many items
+  const int max_ctas = g_decode_variant == 3 ? 4 : 2 * attn_num_sms();
+  const int want = (total + DEC_WARPS - 1) / DEC_WARPS;
+  const int grid = want < max_ctas ? want : max_ctas;
+  kern<<<grid, DEC_WARPS * 32, S_::TOTAL, st>>>((const bf16*)q, q_stride, (bf16*)out,
+                                                (const uint8_t*)kv, bt, bt_stride, ctx, n_seqs, n_q,
+                                                n_kv, n_q / n_kv, scale * 1.4426950408889634f);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
 template <int D, int BS>
 static int launch_prefill(const void* q, int q_stride, void* out, const void* kv,
                           const int32_t* bt, int bt_stride, const int32_t* tiles, int n_tiles,
@@ -478,6 +698,13 @@ using namespace b200q;
 
 extern "C" {
 
+// test/tuning hook: 0 = auto, 1 = split-across-warps kernel, 2 = streaming warp-per-item kernel
+int b200q_decode_attn_set_variant(int v) {
+  B200Q_CHECK_ARG(v >= 0 && v <= 3, "decode variant must be 0..3");
+  g_decode_variant = v;
+  return B200Q_OK;
+}
+
 int b200q_decode_attn(const void* q, int q_stride, void* out, const void* kv_layer,
                       const int32_t* block_table, int bt_stride, const int32_t* ctx_lens,
                       int n_seqs, int n_q, int n_kv, int D, int block_size, float scale,
@@ -490,6 +717,17 @@ int b200q_decode_attn(const void* q, int q_stride, void* out, const void* kv_lay
                   block_size);
   if (n_seqs == 0) return B200Q_OK;
   cudaStream_t st = as_stream(stream);
+  // streaming kernel once every resident warp (2 CTAs x 4 warps per SM) gets >= 2 items
+  const bool stream_variant =
+      g_decode_variant >= 2 ||
+      (g_decode_variant == 0 && (long long)n_seqs * n_kv >= 16LL * attn_num_sms());
+  if (stream_variant) {
+    if (D == 128)
+      return launch_decode_stream<128, 16>(q, q_stride, out, kv_layer, block_table, bt_stride,
+                                           ctx_lens, n_seqs, n_q, n_kv, scale, st);
+    return launch_decode_stream<64, 16>(q, q_stride, out, kv_layer, block_table, bt_stride,
+                                        ctx_lens, n_seqs, n_q, n_kv, scale, st);
+  }
   if (D == 128)
     return launch_decode<128, 16>(q, q_stride, out, kv_layer, block_table, bt_stride, ctx_lens,
                                   n_seqs, n_q, n_kv, scale, st);

@@ -101,6 +101,10 @@ def test_rope_kvwrite(cuda, D, n_q, n_kv):
     assert torch.equal(kvc, expect), "paged KV contents (swizzled layout) must be bit-exact"
 
 
+# Attention tolerance: P is rounded to bf16 before PV in both the kernels and the oracle, but the
+# kernels round exp(s - running_max) page by page while the oracle rounds exp(s - global_max); each
+# term carries 2^-9 relative error, so outputs (|o| ~ 0.1..1 for unit-variance V) agree to ~5e-3
+# absolute / 2 bf16 ulps, whichever is larger.
 def _make_cache(seqs_ctx, n_kv, D, BS, seed):
     """random logical K/V per sequence -> swizzled paged cache + block table"""
     g = torch.Generator().manual_seed(seed)
@@ -146,7 +150,7 @@ def test_decode_attn(cuda, D, n_q, n_kv):
     for i, c in enumerate(ctxs):
         q = qkv[i].float().view(n_q + 2 * n_kv, D)[:n_q][None]
         ref = O.attention(q, ks[i].float(), vs[i].float(), torch.tensor([c - 1]), scale)[0]
-        bf16_close(got[i], ref, ulps=2.0, atol=2e-3, max_mismatch_frac=0.5, what=f"decode ctx={c}")
+        bf16_close(got[i], ref, ulps=2.0, atol=5e-3, max_mismatch_frac=0.5, what=f"decode ctx={c}")
 
 
 @pytest.mark.parametrize("D,n_q,n_kv", [(128, 32, 8), (64, 32, 8)])
@@ -173,7 +177,7 @@ def test_prefill_attn(cuda, D, n_q, n_kv):
     for i, (a, n) in enumerate(chunks):
         q = qkv[row: row + n].float().view(n, n_q + 2 * n_kv, D)[:, :n_q]
         ref = O.attention(q, ks[i].float(), vs[i].float(), torch.arange(a, a + n), scale)
-        bf16_close(got[row: row + n], ref, ulps=2.0, atol=2e-3, max_mismatch_frac=0.5,
+        bf16_close(got[row: row + n], ref, ulps=2.0, atol=5e-3, max_mismatch_frac=0.5,
                    what=f"prefill chunk {i} (ctx {a}+{n})")
         row += n
 
@@ -243,3 +247,32 @@ def test_gemm_swiglu_fused(cuda, M, I, K, mode):
     ref = O.swiglu(gu.float())
     # a 1-ulp flip of g or u (accumulation order) moves the product by about one ulp as well
     bf16_close(out, ref, ulps=8.0, atol=2e-5 * math.sqrt(K), max_mismatch_frac=0.02, what=f"gemm_swiglu mode={mode}")
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("D,n_q,n_kv", [(128, 32, 8), (64, 32, 8), (128, 8, 1)])
+def test_decode_attn_streaming_variant(cuda, D, n_q, n_kv, variant):
+    """persistent warp-per-(sequence, kv-head) kernel; variant 3 forces many items per warp so the
+    page ring runs across item borders (ragged contexts, partial pages, >32-page items)"""
+    from llmq_b200 import lib
+    BS = 16
+    g = np.random.default_rng(4)
+    ctxs = g.integers(1, 90, size=40).tolist() + [1, 16, 17, 255, 129, 600, 513, 32, 48, 1]
+    kv, bt, ks, vs = _make_cache(ctxs, n_kv, D, BS, seed=17)
+    B = len(ctxs)
+    qkv = rnd(B, (n_q + 2 * n_kv) * D, seed=18)
+    out = torch.full((B, n_q * D), float("nan"), dtype=BF, device=cuda)
+    scale = 1.0 / math.sqrt(D)
+    L = lib.load()
+    lib.check(L.b200q_decode_attn_set_variant(variant))
+    try:
+        lib.decode_attn(qkv.to(cuda), out, kv.to(cuda), bt.to(cuda),
+                        torch.tensor(ctxs, dtype=torch.int32, device=cuda), n_q, n_kv, D, BS, scale)
+        torch.cuda.synchronize()
+    finally:
+        lib.check(L.b200q_decode_attn_set_variant(0))
+    got = out.float().cpu().view(B, n_q, D)
+    for i, c in enumerate(ctxs):
+        q = qkv[i].float().view(n_q + 2 * n_kv, D)[:n_q][None]
+        ref = O.attention(q, ks[i].float(), vs[i].float(), torch.tensor([c - 1]), scale)[0]
+        bf16_close(got[i], ref, ulps=2.0, atol=5e-3, max_mismatch_frac=0.5, what=f"decode-stream v{variant} ctx={c}")

@@ -152,6 +152,41 @@ def ncu_targets(f):
     emit(f, kind="ncu_targets", M=M, done=True)
 
 
+def decode_variants(f):
+    """split (v1) vs streaming (v2) decode attention on the bench's shape: B=4608, contexts 129..255"""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n_q, n_kv, D, BS = 32, 8, 128, 16
+    L = lib.load()
+    for B, lo, hi in ((4608, 129, 256), (4608, 192, 193), (1024, 129, 256), (296, 129, 256), (64, 1024, 1025)):
+        g = torch.Generator(device="cpu").manual_seed(0)
+        ctx_list = torch.randint(lo, hi, (B,), generator=g)
+        nb = ((ctx_list + BS - 1) // BS)
+        maxb = int(nb.max())
+        NB = int(nb.sum()) + 1
+        kv = torch.randn(NB, 2, n_kv, BS, D, device=dev).to(BF)
+        perm = torch.randperm(NB - 1) + 1
+        bt = torch.zeros(B, (maxb + 7) // 8 * 8, dtype=torch.int32)
+        off = 0
+        for i in range(B):
+            n = int(nb[i])
+            bt[i, :n] = perm[off:off + n]
+            off += n
+        bt = bt.to(dev)
+        ctxs = ctx_list.to(torch.int32).to(dev)
+        qkv = torch.randn(B, (n_q + 2 * n_kv) * D, device=dev).to(BF)
+        out = torch.empty(B, n_q * D, dtype=BF, device=dev)
+        byts = float(ctx_list.sum()) * n_kv * D * 2 * 2
+        res = dict(kind="decode_variants", B=B, ctx_lo=lo, ctx_hi=hi - 1)
+        for v in (1, 2):
+            L.b200q_decode_attn_set_variant(v)
+            med, best = timeit(lambda: lib.decode_attn(qkv, out, kv, bt, ctxs, n_q, n_kv, D, BS, 1 / math.sqrt(D)), iters=15, flush=flush)
+            res[f"ms_v{v}"] = round(med, 4)
+            res[f"gbs_v{v}"] = round(byts / med / 1e6, 1)
+        L.b200q_decode_attn_set_variant(0)
+        emit(f, **res)
+        del kv
+
+
 def gemm_limits(f):
     """where do the GEMM's bubbles come from?  time the kernel with the operand loads and/or the
     epilogue switched off (results are garbage in those modes; timing only)"""
@@ -294,4 +329,4 @@ if __name__ == "__main__":
     tag = os.environ.get("PROBE_TAG", "")
     with open(os.path.join(OUT, f"probe_{mode}{tag}.jsonl"), "w") as f:
         {"gemm_check": gemm_check, "bench": bench, "gemm2_bench": gemm2_bench, "ncu_targets": ncu_targets,
-         "argmax_ties": argmax_ties, "gemm_limits": gemm_limits}[mode](f)
+         "argmax_ties": argmax_ties, "gemm_limits": gemm_limits, "decode_variants": decode_variants}[mode](f)

@@ -73,6 +73,26 @@ def usable_host_cores() -> int:
     return max(1, min(n, int(os.environ.get("B200Q_CPU_THREADS", "64"))))
 
 
+def ncu_traffic(kernel_substr):
+    """dram read+write bytes per launch of the named kernel from the committed `ncu --set full`
+    capture (profiles/r1_ncu_full_targets.csv: the bench's GEMM shapes at M=4608), or None"""
+    import csv
+
+    p = os.path.join(ROOT, "profiles", "r1_ncu_full_targets.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        hdr, units = rows[0], rows[1]
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        for r in rows[2:]:
+            if kernel_substr in r[ik]:
+                return (float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]],
+                        f"ncu --set full, {kernel_substr} (fused gate_up GEMM, M=4608): algorithmic 405 MB")
+    except Exception:
+        pass
+    return None, "no ncu capture found"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -381,7 +401,8 @@ def run_native(args):
                 "traffic": None, "peak_source": peaks["source"],
                 "launch_avg_ms": round(g["ms"] / max(g["launches"], 1), 5), "launches": g["launches"],
                 "share_of_device_time": shares}
-    roofline_dec = {"bound": "hbm", "kernel": "b200q::decode_attn_kernel<128,16>", "achieved": round(dec_gbs, 1),
+    roofline["traffic"], roofline["traffic_note"] = ncu_traffic("gemm_bf16_kernel<256, 1>")
+    roofline_dec = {"bound": "hbm", "kernel": "b200q::decode_attn_stream_kernel<128,16> (B*n_kv >= 16*SMs) / decode_attn_kernel", "achieved": round(dec_gbs, 1),
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(dec_gbs / peaks["hbm_gbs"], 4),
                     "launch_avg_ms": round(d["ms"] / max(d["launches"], 1), 5), "launches": d["launches"]}
     # whole-step decode HBM roofline fraction: algorithmic bytes per output token

@@ -36,7 +36,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = GEMM_SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : GEMM_SMEM_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
-  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 4096 /*epilogue*/;
 };
 
 // ---- tcgen05 PTX wrappers ------------------------------------------------------------------
@@ -110,55 +110,76 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
          ((uint32_t)(GEMM_BM >> 4) << 24);
 }
 
-// Drain this thread's TMEM lane (one output row of the 128 x BN fp32 accumulator tile) to global.
+// Drain one warp's 32 x BN slice of the fp32 accumulator tile (TMEM lanes 32q..32q+31, one row per
+// thread) to global memory.  Each thread converts 64 columns of its row to bf16 (128 B), the warp
+// transposes them through a 4 KB XOR-swizzled shared-memory patch and stores them back as
+// 4 rows x 128 contiguous bytes per instruction — full 128 B lines instead of 32 scattered 16 B
+// pieces, which matters because the L2 request rate is shared with the TMA operand stream.
 // kSwiGLU (K9+K10 fused): the weight rows were interleaved at load time so that the tile's
 // columns are [gate (BN/2) | up (BN/2)] of the SAME BN/2 output columns; the epilogue applies
 // out = bf16(bf16(silu(bf16(g))) * bf16(u)) — identical rounding points to the unfused path
 // (GEMM output rounded to bf16, then oracle/ops.py::swiglu) — and writes BN/2 columns, so the
 // [T, 2I] intermediate never touches HBM.
+constexpr int EPI_SMEM_PER_WARP = 32 * 128;  // 32 rows x 64 bf16
+
 template <int BN, bool kSwiGLU>
-__device__ __forceinline__ void epilogue_row(uint32_t taddr, bf16* crow, bool valid) {
-  if constexpr (!kSwiGLU) {
+__device__ __forceinline__ void epilogue_rows(uint32_t taddr, bf16* ctile, long long ldc,
+                                              int row0, int M, uint8_t* patch, int lane) {
+  constexpr int OUT_BN = kSwiGLU ? BN / 2 : BN;
+  auto act = [](uint32_t gb, uint32_t ub) -> float {
+    const float g = round_bf16(__uint_as_float(gb)), u = round_bf16(__uint_as_float(ub));
+    return round_bf16(g / (1.f + __expf(-g))) * u;
+  };
+  const uint32_t patch_s = smem_u32(patch);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = 0; c0 < OUT_BN; c0 += 64) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // two 32-column TMEM loads -> 64 output columns of this row
       uint32_t v[32];
-      tmem_ld32(taddr + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (valid) {
+      uint4 o[4];
+      if constexpr (!kSwiGLU) {
+        tmem_ld32(taddr + (uint32_t)(c0 + 32 * h), v);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-          o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-          o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-          o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-          st_v4(crow + c0 + 8 * j, o);
+          o[j].x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+          o[j].y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+          o[j].z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+          o[j].w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
         }
-      }
-    }
-  } else {
-    auto act = [](uint32_t gb, uint32_t ub) -> float {
-      const float g = round_bf16(__uint_as_float(gb)), u = round_bf16(__uint_as_float(ub));
-      return round_bf16(g / (1.f + __expf(-g))) * u;
-    };
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-      uint32_t g[32], u[32];
-      tmem_ld32(taddr + (uint32_t)c0, g);
-      tmem_ld32(taddr + (uint32_t)(BN / 2 + c0), u);
-      tmem_ld_wait();
-      if (valid) {
+      } else {
+        uint32_t u[32];
+        tmem_ld32(taddr + (uint32_t)(c0 + 32 * h), v);
+        tmem_ld32(taddr + (uint32_t)(BN / 2 + c0 + 32 * h), u);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          o.x = pack_bf16x2(act(g[8 * j + 0], u[8 * j + 0]), act(g[8 * j + 1], u[8 * j + 1]));
-          o.y = pack_bf16x2(act(g[8 * j + 2], u[8 * j + 2]), act(g[8 * j + 3], u[8 * j + 3]));
-          o.z = pack_bf16x2(act(g[8 * j + 4], u[8 * j + 4]), act(g[8 * j + 5], u[8 * j + 5]));
-          o.w = pack_bf16x2(act(g[8 * j + 6], u[8 * j + 6]), act(g[8 * j + 7], u[8 * j + 7]));
-          st_v4(crow + c0 + 8 * j, o);
+          o[j].x = pack_bf16x2(act(v[8 * j + 0], u[8 * j + 0]), act(v[8 * j + 1], u[8 * j + 1]));
+          o[j].y = pack_bf16x2(act(v[8 * j + 2], u[8 * j + 2]), act(v[8 * j + 3], u[8 * j + 3]));
+          o[j].z = pack_bf16x2(act(v[8 * j + 4], u[8 * j + 4]), act(v[8 * j + 5], u[8 * j + 5]));
+          o[j].w = pack_bf16x2(act(v[8 * j + 6], u[8 * j + 6]), act(v[8 * j + 7], u[8 * j + 7]));
         }
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // chunk (4h + j) of this thread's 128 B row
+        const uint32_t a = patch_s + lane * 128 + (((4 * h + j) ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o[j].x), "r"(o[j].y),
+                     "r"(o[j].z), "r"(o[j].w)
+                     : "memory");
+      }
     }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // 4 rows x 128 B per instruction
+      const int rr = i * 4 + (lane >> 3), c = lane & 7;
+      uint4 o;
+      const uint32_t a = patch_s + rr * 128 + ((c ^ (rr & 7)) << 4);
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                   : "r"(a));
+      if (row0 + rr < M) st_v4(ctile + (long long)rr * ldc + c0 + c * 8, o);
+    }
+    __syncwarp();
   }
 }
 
@@ -177,6 +198,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tmem_full = empty + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 256;  // 4 warps x 4 KB transpose patches
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
@@ -273,12 +295,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + quarter * 32 + lane;
+      const int row0 = m_blk * GEMM_BM + quarter * 32;
       constexpr int OUT_BN = kSwiGLU ? BN / 2 : BN;
       const long long ldc = kSwiGLU ? N / 2 : N;
-      bf16* crow = C + (long long)row * ldc + (long long)n_blk * OUT_BN;
+      bf16* ctile = C + (long long)row0 * ldc + (long long)n_blk * OUT_BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      if (!(dbg & 2)) epilogue_row<BN, kSwiGLU>(taddr, crow, row < M);  // dbg&2: skip the drain
+      if (!(dbg & 2))  // dbg&2: skip the drain (timing experiment)
+        epilogue_rows<BN, kSwiGLU>(taddr, ctile, ldc, row0, M, epi_smem + (warp - 2) * EPI_SMEM_PER_WARP, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
@@ -310,7 +333,7 @@ struct Gemm2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = GEMM_SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : GEMM_SMEM_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + 4 * 4096;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -396,6 +419,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tmem_full = empty + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 256;  // 4 warps x 4 KB transpose patches
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -498,12 +522,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
-      const int row = m_blk * 256 + (int)rank * 128 + quarter * 32 + lane;
+      const int row0 = m_blk * 256 + (int)rank * 128 + quarter * 32;
       constexpr int OUT_BN = kSwiGLU ? BN / 2 : BN;
       const long long ldc = kSwiGLU ? N / 2 : N;
-      bf16* crow = C + (long long)row * ldc + (long long)n_blk * OUT_BN;
+      bf16* ctile = C + (long long)row0 * ldc + (long long)n_blk * OUT_BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      if (!(dbg & 2)) epilogue_row<BN, kSwiGLU>(taddr, crow, row < M);  // dbg&2: skip the drain
+      if (!(dbg & 2))  // dbg&2: skip the drain (timing experiment)
+        epilogue_rows<BN, kSwiGLU>(taddr, ctile, ldc, row0, M, epi_smem + (warp - 2) * EPI_SMEM_PER_WARP, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tmem_empty + acc, 0));

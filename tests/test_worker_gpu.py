@@ -1,0 +1,89 @@
+"""The drop-in itself on a B200: the reference's BaseWorker / BrokerManager (unmodified, from
+baseline/_ref or /root/reference) + B200Worker loading a model DIRECTORY (config.json, safetensors,
+tokenizer files — what `llmq worker run <model> <queue>` gets), jobs in through the broker,
+results out of `<queue>.results`, texts compared with the CPU oracle's greedy decode."""
+import asyncio
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "shims"))
+for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+    if os.path.isdir(os.path.join(p, "llmq")):
+        sys.path.insert(0, p)
+        break
+os.environ.setdefault("LLMQ_LOG_LEVEL", "WARNING")
+
+
+def test_b200_worker_end_to_end_from_model_dir(cuda, tmp_path, monkeypatch):
+    import aio_pika
+    from llmq.core.broker import BrokerManager
+    from llmq.core.models import Job, Result
+
+    from llmq_b200.fixtures import seeded_state_dict, write_model_dir
+    from llmq_b200.model import ModelSpec
+    from llmq_b200.worker import B200Worker
+    from oracle.model import LlamaDims, LlamaOracle
+
+    spec = ModelSpec(hidden=512, n_layers=2, n_q_heads=8, n_kv_heads=2, head_dim=128, intermediate=1024,
+                     vocab=2048, max_position_embeddings=256, name="tiny")
+    mdir = write_model_dir(str(tmp_path / "tiny-llama"), spec, seed=77, with_weights=True)
+    monkeypatch.setenv("VLLM_MAX_TOKENS", "10")
+    monkeypatch.setenv("VLLM_MAX_NUM_SEQS", "8")
+    monkeypatch.setenv("VLLM_MAX_MODEL_LEN", "256")
+    monkeypatch.setenv("VLLM_GPU_MEMORY_UTILIZATION", "0.05")
+    monkeypatch.setenv("B200Q_MAX_NUM_BATCHED_TOKENS", "256")
+    aio_pika.reset_brokers()
+
+    async def main():
+        w = B200Worker(mdir, "gq", tensor_parallel_size=1)
+        task = asyncio.create_task(w.run())
+        b = BrokerManager()
+        await b.connect()
+        await b.setup_queue_infrastructure("gq")
+        jobs = [Job(id=f"j{i}", prompt="w5 {x} w9", x=f"w{20 + i}", tag=i) for i in range(12)]
+        jobs.append(Job(id="chat", messages=[{"role": "user", "content": "w5 w6 w7"}]))
+        jobs.append(Job(id="long", prompt=" ".join(["w11"] * 300)))  # > VLLM_MAX_MODEL_LEN: dropped
+        for j in jobs:
+            await b.publish_job("gq", j)
+        got = {}
+
+        async def on_res(m):
+            r = Result.parse_raw(m.body)
+            got[r.id] = r
+            await m.ack()
+
+        await b.consume_results("gq", on_res)
+        for _ in range(600):
+            if len(got) >= len(jobs) - 1:
+                break
+            await asyncio.sleep(0.05)
+        tok = w.service.tokenizer
+        w.running = False
+        await asyncio.wait_for(task, 30)
+        return got, tok
+
+    got, tok = asyncio.run(main())
+    assert "long" not in got and len(got) == 13
+    sd = seeded_state_dict(spec, 77)
+    oracle = LlamaOracle(LlamaDims.from_hf_config(spec.to_hf_config()), sd, "bf16", max_pos=256)
+    n_exact = 0
+    for i in range(12):
+        ids = tok(f"w5 w{20 + i} w9", add_special_tokens=True).input_ids
+        ref, lg = oracle.greedy(ids, 10, eos_id=tok.eos_token_id, return_logits=True)
+        ref_text = tok.decode(ref, skip_special_tokens=True)
+        r = got[f"j{i}"]
+        assert r.prompt == f"w5 w{20 + i} w9" and r.model_dump()["tag"] == i and r.worker_id.startswith("b200-")
+        if r.result == ref_text:
+            n_exact += 1
+        else:  # allowed only from a bf16 near-tie onwards
+            out = tok(r.result, add_special_tokens=False).input_ids
+            k = next((j for j in range(min(len(out), len(ref))) if out[j] != ref[j]), min(len(out), len(ref)))
+            top2 = lg[min(k, len(lg) - 1)].topk(2).values
+            assert (top2[0] - top2[1]).item() < 0.12, (i, k, r.result, ref_text)
+    assert n_exact >= 9, f"only {n_exact}/12 texts identical to the oracle's"
+    assert got["chat"].prompt == "Chat with 1 messages" and isinstance(got["chat"].result, str)

@@ -306,6 +306,7 @@ def run_native(args):
 
     # ---- arm B: end to end through the worker-facing service call (host text in / text out) ----
     os.environ["VLLM_MAX_TOKENS"] = str(args.out_tokens)
+    os.environ["B200Q_TEMPERATURE"] = "0"  # the workload is greedy (oracle mode); the worker's default is 0.7
     os.environ.setdefault("LLMQ_LOG_LEVEL", "WARNING")
     ensure_llmq_importable()
     from llmq.core.models import Job

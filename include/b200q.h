@@ -113,6 +113,15 @@ int b200q_gather_rows(const void* x_dev, const int32_t* rows_dev, void* out_dev,
  *     (vllm/v1/sample/sampler.py:91,235-236 in the oracle's temperature-0 mode) */
 int b200q_argmax_bf16(const void* logits_dev, int32_t* ids_dev, int B, int V, void* stream);
 
+/* K13 sampler, the reference's default (temperature 0.7, no top-p/k;
+ *     ref:llmq/workers/vllm_worker.py:161-165; vllm/v1/sample/ops/topk_topp_sampler.py:395-416:
+ *     probs.div_(q).argmax, q ~ Exp(1)): ids[b] = argmax_v (logits[b,v]/T_b - log q_bv) with
+ *     q_bv = -log(u), u from Philox4x32-10(key = seed_b, counter = (v/4, position_b, 0, 0)).
+ *     params_dev: int32[B][4] = {float bits of temperature, seed lo, seed hi, position};
+ *     temperature <= 0 selects the greedy argmax for that row. */
+int b200q_sample_bf16(const void* logits_dev, const int32_t* params_dev, int32_t* ids_dev,
+                      int B, int V, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Model-level: one forward step over a mixed decode+prefill token batch.
  * Replaces GPUModelRunner.execute_model for LlamaForCausalLM
@@ -153,6 +162,8 @@ typedef struct b200q_batch {
   const int32_t* tiles;         /* [n_tiles][4]                                                 */
   const int32_t* sample_rows;   /* [n_sample] batch rows whose hidden state feeds the LM head   */
   int32_t* out_ids;             /* [n_sample] sampled token ids                                 */
+  const int32_t* sample_params; /* [n_sample][4] {temperature bits, seed lo, seed hi, position};
+                                   NULL = greedy argmax for every row                           */
   /* host-side bookkeeping for the profiler (algorithmic work of this step's attention) */
   int64_t sum_ctx_dec;          /* sum of ctx_lens over the decode sequences                    */
   int64_t prefill_flops_per_layer; /* causal QK^T + PV flops of the prefill tiles, one layer     */
@@ -236,6 +247,12 @@ int b200q_engine_destroy(b200q_engine_t e);
  * turns that into ValueError => job dropped, ref:llmq/workers/base.py:228-235). */
 int b200q_engine_add_request(b200q_engine_t e, int64_t req_id, const int32_t* prompt_ids,
                              int32_t n_prompt, int32_t max_new_tokens, int32_t ignore_eos);
+/* same, with the sampling the reference worker uses: temperature (0 = greedy) and a per-request
+ * seed; token t of the request is drawn with Philox counter position t, so the result does not
+ * depend on batching, chunking or preemption. */
+int b200q_engine_add_request_sampled(b200q_engine_t e, int64_t req_id, const int32_t* prompt_ids,
+                                     int32_t n_prompt, int32_t max_new_tokens, int32_t ignore_eos,
+                                     float temperature, uint64_t seed);
 int b200q_engine_abort(b200q_engine_t e, int64_t req_id);
 /* 1 if any request is waiting or running */
 int b200q_engine_has_work(b200q_engine_t e);

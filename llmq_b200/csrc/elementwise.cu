@@ -274,6 +274,100 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K13 sampler at temperature > 0: the reference's default path (SamplingParams(temperature=0.7),
+// ref:llmq/workers/vllm_worker.py:161-165; vLLM: probs = softmax(logits/T); probs.div_(q).argmax
+// with q ~ Exp(1), vllm/v1/sample/ops/topk_topp_sampler.py:395-416).  argmax_i p_i/q_i ==
+// argmax_i (logit_i/T - log q_i), so no softmax pass is needed: one read of the bf16 logits row.
+// q_i = -log(u_i), u_i from Philox4x32-10 keyed by the request's seed with counter
+// (element index / 4, token position) — counter-based, so a request's samples do not depend on
+// its batch-mates.  temperature == 0 rows fall back to the greedy argmax (lowest index on ties).
+// params: int32[B][4] = {float bits of temperature, seed lo, seed hi, position}.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+__device__ __forceinline__ float gumbel_from_bits(uint32_t x) {
+  const float u = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1), 24 bits
+  return -logf(-logf(u));
+}
+
+__global__ void __launch_bounds__(1024)
+    sample_kernel(const bf16* __restrict__ logits, const int32_t* __restrict__ params,
+                  int32_t* __restrict__ ids, int V) {
+  const bf16* row = logits + (long long)blockIdx.x * V;
+  const float temp = __int_as_float(params[4 * blockIdx.x + 0]);
+  const uint32_t k0 = (uint32_t)params[4 * blockIdx.x + 1], k1 = (uint32_t)params[4 * blockIdx.x + 2];
+  const uint32_t pos = (uint32_t)params[4 * blockIdx.x + 3];
+  const bool greedy = !(temp > 0.f);
+  const float inv_t = greedy ? 1.f : 1.f / temp;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  // groups of 4 consecutive elements share one Philox block: counter = (group, position, 0, 0)
+  const int n4 = V / 4;
+  for (int g = threadIdx.x; g < n4; g += blockDim.x) {
+    const uint2 a = *reinterpret_cast<const uint2*>(row + 4 * g);  // 4 bf16 (V*2 B rows are 8 B aligned)
+    float v[4] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y)};
+    if (!greedy) {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)g, pos, 0u, 0u, k0, k1, r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = v[k] * inv_t + gumbel_from_bits(r[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) amax_update(v[k], 4 * g + k, best, bi);
+  }
+  for (int i = n4 * 4 + threadIdx.x; i < V; i += blockDim.x) {  // tail (V % 4 elements)
+    float v = __bfloat162float(row[i]);
+    if (!greedy) {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)(i / 4), pos, 0u, 0u, k0, k1, r);
+      v = v * inv_t + gumbel_from_bits(r[i & 3]);
+    }
+    amax_update(v, i, best, bi);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    amax_update(ov, oi, best, bi);
+  }
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  if ((threadIdx.x & 31) == 0) {
+    sv[threadIdx.x >> 5] = best;
+    si[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -INFINITY;
+    bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      amax_update(ov, oi, best, bi);
+    }
+    if (threadIdx.x == 0) ids[blockIdx.x] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
 static inline int grid_for(long long items, int threads) {
   long long b = (items + threads - 1) / threads;
   const long long cap = 148LL * 16;  // 16 resident 256-thread CTAs per SM
@@ -375,6 +469,16 @@ int b200q_argmax_bf16(const void* logits, int32_t* ids, int B, int V, void* stre
   B200Q_CHECK_ARG(B >= 0 && V > 0, "argmax: bad shape B=%d V=%d", B, V);
   if (B == 0) return B200Q_OK;
   argmax_kernel<<<B, 1024, 0, as_stream(stream)>>>((const bf16*)logits, ids, V);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
+int b200q_sample_bf16(const void* logits, const int32_t* params, int32_t* ids, int B, int V,
+                      void* stream) {
+  B200Q_CHECK_ARG(B >= 0 && V > 0 && V % 4 == 0, "sample: bad shape B=%d V=%d (V %% 4 == 0)", B, V);
+  B200Q_CHECK_ARG(params != nullptr, "sample: params is null");
+  if (B == 0) return B200Q_OK;
+  sample_kernel<<<B, 1024, 0, as_stream(stream)>>>((const bf16*)logits, params, ids, V);
   B200Q_LAUNCH_CHECK();
   return B200Q_OK;
 }

@@ -13,6 +13,8 @@
 // int32 metadata (token ids, positions, slot mapping, context lengths, prefill q-tiles, sample
 // rows, block table), ships it with one H2D copy, runs the forward on the engine's stream and
 // reads back the sampled ids with one D2H copy.
+#include <string.h>
+
 #include <algorithm>
 #include <deque>
 #include <unordered_map>
@@ -38,6 +40,8 @@ struct Request {
   int32_t max_new;
   bool ignore_eos;
   std::vector<int32_t> blocks;
+  float temperature = 0.f;      // 0 = greedy
+  uint64_t seed = 0;
   int32_t n_sched = 0;          // tokens scheduled in the current step
   int32_t sample_slot = -1;     // index into out_ids for this step, or -1
 };
@@ -112,7 +116,7 @@ int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b20
   const int64_t T = cfg->max_num_batched_tokens, S = cfg->max_num_seqs;
   // token_ids, positions, slot_mapping [T each]; ctx_lens [S]; sample_rows [S];
   // tiles [4 * (T/16 + S)]; block table [S * max_blocks_per_seq]
-  e->meta_cap = 3 * T + 2 * S + 4 * (T / 16 + S + 2) +
+  e->meta_cap = 3 * T + 2 * S + 4 * S + 8 + 4 * (T / 16 + S + 2) +
                 S * (int64_t)((e->max_blocks_per_seq + 7) & ~7) + 64;
   cudaError_t ce;
   if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -169,6 +173,18 @@ int b200q_engine_add_request(b200q_engine_t e, int64_t req_id, const int32_t* pr
   r->ignore_eos = ignore_eos != 0;
   e->by_id[req_id] = r;
   e->waiting.push_back(r);
+  return B200Q_OK;
+}
+
+int b200q_engine_add_request_sampled(b200q_engine_t e, int64_t req_id, const int32_t* prompt_ids,
+                                     int32_t n_prompt, int32_t max_new_tokens, int32_t ignore_eos,
+                                     float temperature, uint64_t seed) {
+  B200Q_CHECK_ARG(temperature >= 0.f && temperature == temperature, "add_request: bad temperature");
+  int rc = b200q_engine_add_request(e, req_id, prompt_ids, n_prompt, max_new_tokens, ignore_eos);
+  if (rc) return rc;
+  Request* r = e->by_id[req_id];
+  r->temperature = temperature;
+  r->seed = seed;
   return B200Q_OK;
 }
 
@@ -313,9 +329,11 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
   int32_t* slot = pos + T;
   int32_t* ctx = slot + T;
   int32_t* srows = ctx + n_dec;
-  int32_t* tiles = srows + n_rows;  // reserve n_rows sample slots
-  tiles += (4 - ((tiles - e->h_meta) & 3)) & 3;  // the prefill kernel reads tiles as int4
+  int32_t* sparams = srows + n_rows;  // reserve n_rows sample slots
+  sparams += (4 - ((sparams - e->h_meta) & 3)) & 3;
+  int32_t* tiles = sparams + 4 * n_rows;  // 16-byte aligned: the prefill kernel reads tiles as int4
   int n_tiles = 0, n_sample = 0, row = 0;
+  bool any_sampled = false;
   // count tiles first to place the block table after them
   for (Request* r : sched)
     if (r->n_sched > 1) n_tiles += (r->n_sched + 15) / 16;
@@ -351,6 +369,14 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     }
     if (r->n_computed + r->n_sched == (int)r->tokens.size()) {
       r->sample_slot = n_sample;
+      float tf = r->temperature;
+      int32_t tbits;
+      memcpy(&tbits, &tf, 4);
+      sparams[4 * n_sample + 0] = tbits;
+      sparams[4 * n_sample + 1] = (int32_t)(uint32_t)(r->seed & 0xffffffffu);
+      sparams[4 * n_sample + 2] = (int32_t)(uint32_t)(r->seed >> 32);
+      sparams[4 * n_sample + 3] = r->n_generated;  // Philox counter: index of the token being drawn
+      any_sampled |= tf > 0.f;
       srows[n_sample++] = row + r->n_sched - 1;
     } else {
       r->sample_slot = -1;
@@ -381,6 +407,7 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
   b.tiles = e->d_meta + (tiles - e->h_meta);
   b.block_table = e->d_meta + (btab - e->h_meta);
   b.out_ids = e->d_out;
+  b.sample_params = any_sampled ? e->d_meta + (sparams - e->h_meta) : nullptr;
   b.sum_ctx_dec = 0;
   b.prefill_flops_per_layer = 0;
   for (Request* r : sched) {

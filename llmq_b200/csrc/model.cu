@@ -300,7 +300,12 @@ int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
     B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, m->final_norm, T, H, c.rms_eps, stream));
     B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * b->n_sample * H * 2, b200q_gather_rows(m->x, b->sample_rows, m->sel, b->n_sample, H, stream));
     B200Q_TRY(B200Q_PROF_GEMM, 2.0 * b->n_sample * (double)c.vocab * H, b200q_gemm_bf16(m->sel, m->lm_head, m->logits, b->n_sample, c.vocab, H, stream));
-    B200Q_TRY(B200Q_PROF_ELEMENTWISE, (double)b->n_sample * c.vocab * 2, b200q_argmax_bf16(m->logits, b->out_ids, b->n_sample, c.vocab, stream));
+    if (b->sample_params)
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, (double)b->n_sample * c.vocab * 2,
+                b200q_sample_bf16(m->logits, b->sample_params, b->out_ids, b->n_sample, c.vocab, stream));
+    else
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, (double)b->n_sample * c.vocab * 2,
+                b200q_argmax_bf16(m->logits, b->out_ids, b->n_sample, c.vocab, stream));
   }
 #undef B200Q_TRY
   return B200Q_OK;

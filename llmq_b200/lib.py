@@ -57,6 +57,7 @@ class Batch(C.Structure):
         ("tiles", C.c_void_p),
         ("sample_rows", C.c_void_p),
         ("out_ids", C.c_void_p),
+        ("sample_params", C.c_void_p),
         ("sum_ctx_dec", C.c_int64),
         ("prefill_flops_per_layer", C.c_int64),
     ]
@@ -119,6 +120,7 @@ SIGNATURES = {
     "b200q_swiglu": (_i, [_vp, _vp, _i, _i, _vp]),
     "b200q_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "b200q_argmax_bf16": (_i, [_vp, _vp, _i, _i, _vp]),
+    "b200q_sample_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "b200q_model_create": (_i, [C.POINTER(ModelConfig), C.POINTER(_vp)]),
     "b200q_model_destroy": (_i, [_vp]),
     "b200q_model_bind_weight": (_i, [_vp, C.c_char_p, _vp, _i64, _i64]),
@@ -134,6 +136,7 @@ SIGNATURES = {
     "b200q_engine_create": (_i, [_vp, C.POINTER(EngineConfig), C.POINTER(_vp)]),
     "b200q_engine_destroy": (_i, [_vp]),
     "b200q_engine_add_request": (_i, [_vp, _i64, _vp, C.c_int32, C.c_int32, C.c_int32]),
+    "b200q_engine_add_request_sampled": (_i, [_vp, _i64, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64]),
     "b200q_engine_abort": (_i, [_vp, _i64]),
     "b200q_engine_has_work": (_i, [_vp]),
     "b200q_engine_step": (_i, [_vp, _vp, _vp, _vp, C.c_int32, C.POINTER(C.c_int32)]),
@@ -257,6 +260,11 @@ def swiglu(gate_up, out, stream=None):
 
 def gather_rows(x, rows, out, stream=None):
     check(load().b200q_gather_rows(_p(x), _p(rows), _p(out), rows.numel(), x.shape[1], _stream(stream)))
+
+
+def sample_bf16(logits, params, ids, stream=None):
+    """params: int32 [B,4] = (temperature float bits, seed lo, seed hi, position)"""
+    check(load().b200q_sample_bf16(_p(logits), _p(params), _p(ids), logits.shape[0], logits.shape[1], _stream(stream)))
 
 
 def argmax_bf16(logits, ids, stream=None):

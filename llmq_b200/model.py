@@ -301,10 +301,14 @@ class Engine:
         self._tok = np.zeros(self.cap, dtype=np.int32)
         self._flg = np.zeros(self.cap, dtype=np.int32)
 
-    def add_request(self, req_id: int, prompt_ids, max_new_tokens: int, ignore_eos: bool = False):
+    def add_request(self, req_id: int, prompt_ids, max_new_tokens: int, ignore_eos: bool = False,
+                    temperature: float = 0.0, seed: int = 0):
+        """temperature 0 = greedy; > 0 = the reference's sampling (softmax(logits/T), exponential race)
+        with a per-request Philox seed"""
         arr = self.np.ascontiguousarray(prompt_ids, dtype=self.np.int32)
-        rc = self.lib.b200q_engine_add_request(self.handle, int(req_id), arr.ctypes.data, arr.size,
-                                               int(max_new_tokens), int(ignore_eos))
+        rc = self.lib.b200q_engine_add_request_sampled(
+            self.handle, int(req_id), arr.ctypes.data, arr.size, int(max_new_tokens), int(ignore_eos),
+            float(temperature), int(seed) & 0xFFFFFFFFFFFFFFFF)
         if rc == -1:  # B200Q_EINVAL: an un-servable job, the worker drops it (ValueError)
             raise ValueError(self.lib.b200q_last_error().decode())
         L.check(rc)

@@ -20,11 +20,13 @@ from . import lib as L
 
 
 class _Req:
-    __slots__ = ("rid", "prompt_ids", "max_new", "stop", "future", "out_ids", "text_len", "loop")
+    __slots__ = ("rid", "prompt_ids", "max_new", "stop", "future", "out_ids", "text_len", "loop",
+                 "temperature", "seed")
 
-    def __init__(self, rid, prompt_ids, max_new, stop, future, loop):
+    def __init__(self, rid, prompt_ids, max_new, stop, future, loop, temperature=0.0, seed=0):
         self.rid, self.prompt_ids, self.max_new, self.stop = rid, prompt_ids, max_new, stop
         self.future, self.loop = future, loop
+        self.temperature, self.seed = temperature, seed
         self.out_ids: List[int] = []
         self.text_len = 0
 
@@ -40,6 +42,9 @@ class GenerationService:
         self._inbox: "queue.SimpleQueue[_Req]" = queue.SimpleQueue()
         self._reqs: Dict[int, _Req] = {}
         self._next_id = 0
+        # B200Q_SEED pins the per-request streams (reproducible runs); default: fresh entropy
+        env_seed = os.environ.get("B200Q_SEED")
+        self._base_seed = int(env_seed) if env_seed else int.from_bytes(os.urandom(8), "little")
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, name="b200q-engine", daemon=True)
         self.error: Optional[BaseException] = None
@@ -58,12 +63,17 @@ class GenerationService:
 
     # ---- called on the event-loop thread ----
     def submit(self, prompt_ids: List[int], max_new: int, stop: Optional[List[str]],
-               loop: asyncio.AbstractEventLoop) -> "asyncio.Future":
+               loop: asyncio.AbstractEventLoop, temperature: float = 0.0,
+               seed: Optional[int] = None) -> "asyncio.Future":
+        """temperature 0 = greedy; > 0 = softmax(logits/T) sampling (the reference default is 0.7).
+        seed None = a fresh stream per request (unseeded, like the reference)."""
         if self.error is not None:
             raise RuntimeError(f"engine thread died: {self.error!r}")
         fut = loop.create_future()
         self._next_id += 1
-        self._inbox.put(_Req(self._next_id, prompt_ids, max_new, stop, fut, loop))
+        if seed is None:
+            seed = (self._base_seed + 0x9E3779B97F4A7C15 * self._next_id) & 0xFFFFFFFFFFFFFFFF
+        self._inbox.put(_Req(self._next_id, prompt_ids, max_new, stop, fut, loop, temperature, seed))
         return fut
 
     # ---- engine thread ----
@@ -116,7 +126,8 @@ class GenerationService:
                         if self.first_submit_t is None:
                             self.first_submit_t = time.perf_counter()
                         try:
-                            eng.add_request(r.rid, r.prompt_ids, r.max_new, ignore_eos=False)
+                            eng.add_request(r.rid, r.prompt_ids, r.max_new, ignore_eos=False,
+                                            temperature=r.temperature, seed=r.seed)
                             self._reqs[r.rid] = r
                         except ValueError as e:  # un-servable job => dropped by the base class
                             self._finish(batch, r, exc=e)

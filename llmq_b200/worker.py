@@ -91,7 +91,14 @@ class B200Worker(BaseWorker):
         ids = self.service.tokenizer(prompt, add_special_tokens=True).input_ids
         extra = job.model_dump()
         max_new = int(extra.get("max_tokens") or self.config.vllm_max_tokens)
-        fut = self.service.submit(ids, max_new, self.stop_strings(job), asyncio.get_running_loop())
+        # the reference hard-codes temperature=0.7, unseeded (vllm_worker.py:161-165); a job may
+        # carry `temperature` / `seed` extras, B200Q_TEMPERATURE overrides the default (0 = greedy)
+        temperature = extra.get("temperature")
+        if temperature is None:
+            temperature = float(os.environ.get("B200Q_TEMPERATURE", "0.7"))
+        seed = extra.get("seed")
+        fut = self.service.submit(ids, max_new, self.stop_strings(job), asyncio.get_running_loop(),
+                                  temperature=float(temperature), seed=None if seed is None else int(seed))
         text, _n = await fut
         return text
 

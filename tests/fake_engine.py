@@ -19,7 +19,8 @@ class FakeEngine:
         self.steps = 0
         self.max_batch_seen = 0
 
-    def add_request(self, rid, ids, max_new, ignore_eos=False):
+    def add_request(self, rid, ids, max_new, ignore_eos=False, temperature=0.0, seed=0):
+        self.last_sampling = (temperature, seed)
         ids = list(ids)
         if len(ids) >= self.max_model_len:
             raise ValueError(f"prompt of {len(ids)} tokens does not fit max_model_len={self.max_model_len}")

@@ -105,6 +105,8 @@ def test_end_to_end_through_reference_base_worker_and_broker(patched):
     assert got["chat"].prompt == "Chat with 1 messages"
     assert got["stop"].result == "w101 w102 "  # cut right before the stop string (no stripping, as vLLM); generation aborted
     assert got["per-job-cap"].result == "w201 w202"
+    # default sampling = the reference's literal temperature 0.7, unseeded (a stream per request)
+    assert eng.last_sampling[0] == pytest.approx(0.7) and eng.last_sampling[1] != 0
     assert w.jobs_processed == 23
 
 

@@ -35,7 +35,7 @@ def test_b200_worker_end_to_end_from_model_dir(cuda, tmp_path, monkeypatch):
     monkeypatch.setenv("VLLM_MAX_TOKENS", "10")
     monkeypatch.setenv("VLLM_MAX_NUM_SEQS", "8")
     monkeypatch.setenv("VLLM_MAX_MODEL_LEN", "256")
-    monkeypatch.setenv("VLLM_GPU_MEMORY_UTILIZATION", "0.05")
+    monkeypatch.setenv("VLLM_GPU_MEMORY_UTILIZATION", "0.3")
     monkeypatch.setenv("B200Q_MAX_NUM_BATCHED_TOKENS", "256")
     aio_pika.reset_brokers()
 

@@ -45,7 +45,12 @@ def test_b200_worker_end_to_end_from_model_dir(cuda, tmp_path, monkeypatch):
         b = BrokerManager()
         await b.connect()
         await b.setup_queue_infrastructure("gq")
-        jobs = [Job(id=f"j{i}", prompt="w5 {x} w9", x=f"w{20 + i}", tag=i) for i in range(12)]
+        # greedy for the oracle comparison: B200Q_TEMPERATURE=0 for j0..j5, a per-job `temperature`
+        # extra for j6..j11 (the worker's default is the reference's 0.7, exercised by "sampled")
+        jobs = [Job(id=f"j{i}", prompt="w5 {x} w9", x=f"w{20 + i}", tag=i, temperature=0) for i in range(12)]
+        jobs.append(Job(id="sampled", prompt="w5 w6", seed=5))
+        jobs.append(Job(id="sampled-again", prompt="w5 w6", seed=5))
+        jobs.append(Job(id="sampled-other", prompt="w5 w6", seed=6))
         jobs.append(Job(id="chat", messages=[{"role": "user", "content": "w5 w6 w7"}]))
         jobs.append(Job(id="long", prompt=" ".join(["w11"] * 300)))  # > VLLM_MAX_MODEL_LEN: dropped
         for j in jobs:
@@ -68,7 +73,9 @@ def test_b200_worker_end_to_end_from_model_dir(cuda, tmp_path, monkeypatch):
         return got, tok
 
     got, tok = asyncio.run(main())
-    assert "long" not in got and len(got) == 13
+    assert "long" not in got and len(got) == 16
+    assert got["sampled"].result == got["sampled-again"].result  # same prompt + seed => same draw
+    assert len(got["sampled"].result.split()) >= 1
     sd = seeded_state_dict(spec, 77)
     oracle = LlamaOracle(LlamaDims.from_hf_config(spec.to_hf_config()), sd, "bf16", max_pos=256)
     n_exact = 0

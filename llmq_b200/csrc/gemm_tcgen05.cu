@@ -187,7 +187,11 @@ template <int BN, bool kSwiGLU = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b, bf16* __restrict__ C, int M,
-                     int N, int K, int dbg) {
+                     int N, int K, int dbg, int splits, float* __restrict__ ws) {
+  // splits > 1 (split-K for decode-sized M, where a projection has too few output tiles to put
+  // every SM on the weight stream): tile space = m x split x n, each CTA accumulates K/splits of
+  // the reduction and writes an fp32 partial tile to ws[split][M][N]; splitk_reduce_kernel sums the
+  // partials in a fixed order (deterministic) and rounds to bf16.
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -203,8 +207,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = N / BN;
-  const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = K / GEMM_BK;
+  const int num_tiles = m_tiles * n_tiles * splits;
+  const int k_blocks = (K / GEMM_BK) / splits;  // k-blocks per tile (per split)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -232,7 +236,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        const int m_blk = tile % m_tiles, rest = tile / m_tiles;
+        const int n_blk = rest / splits, kb0 = (rest % splits) * k_blocks;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty + stage, phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -241,8 +246,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             mbar_arrive(full + stage);
           } else {
             mbar_expect_tx(full + stage, Cfg::STAGE_BYTES);
-            tma_load_2d(sa, &tmap_a, kb * GEMM_BK, m_blk * GEMM_BM, full + stage);
-            tma_load_2d(sb, &tmap_b, kb * GEMM_BK, n_blk * BN, full + stage);
+            tma_load_2d(sa, &tmap_a, (kb0 + kb) * GEMM_BK, m_blk * GEMM_BM, full + stage);
+            tma_load_2d(sb, &tmap_b, (kb0 + kb) * GEMM_BK, n_blk * BN, full + stage);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -292,7 +297,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      const int m_blk = tile % m_tiles, rest = tile / m_tiles;
+      const int n_blk = rest / splits, split = rest % splits;
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
       const int row0 = m_blk * GEMM_BM + quarter * 32;
@@ -300,8 +306,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const long long ldc = kSwiGLU ? N / 2 : N;
       bf16* ctile = C + (long long)row0 * ldc + (long long)n_blk * OUT_BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      if (!(dbg & 2))  // dbg&2: skip the drain (timing experiment)
+      if (splits > 1) {
+        // fp32 partial of this K-slice: ws[split][row][col]; one full 128 B line per thread per load
+        const int row = row0 + lane;
+        float* wrow = ws + ((long long)split * M + row) * N + (long long)n_blk * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (row < M) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_v4(wrow + c0 + 4 * j, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          }
+        }
+      } else if (!(dbg & 2)) {  // dbg&2: skip the drain (timing experiment)
         epilogue_rows<BN, kSwiGLU>(taddr, ctile, ldc, row0, M, epi_smem + (warp - 2) * EPI_SMEM_PER_WARP, lane);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
@@ -315,6 +337,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// out[m][n] = bf16(sum_s ws[s][m][n]), partials added in split order (deterministic)
+__global__ void __launch_bounds__(256)
+    splitk_reduce_kernel(const float4* __restrict__ ws, uint4* __restrict__ out, long long mn8,
+                         int splits) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < mn8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 a = ws[2 * i], b = ws[2 * i + 1];
+    for (int s = 1; s < splits; ++s) {
+      const float4 c = ws[2 * (i + (long long)s * mn8)], d = ws[2 * (i + (long long)s * mn8) + 1];
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y);
+    o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y);
+    o.w = pack_bf16x2(b.z, b.w);
+    out[i] = o;
   }
 }
 
@@ -639,9 +682,12 @@ static int num_sms() {
 
 static int g_gemm_debug = 0;  // timing experiments only (wrong results): 1 = no TMA loads, 2 = no epilogue
 
+static float* g_splitk_ws = nullptr;
+static size_t g_splitk_ws_bytes = 0;
+
 template <int BN, bool kSwiGLU = false>
 static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int K,
-                       cudaStream_t st) {
+                       cudaStream_t st, int splits = 1) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
   int rc = get_tmap(A, M, K, GEMM_BM, &ta);
@@ -655,10 +701,28 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     attr_set = true;
   }
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN) * splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K, g_gemm_debug);
+  float* ws = nullptr;
+  if (splits > 1) {
+    const size_t need = (size_t)splits * M * N * sizeof(float);
+    if (need > g_splitk_ws_bytes) {  // grow-only scratch owned by the library
+      if (g_splitk_ws) cudaFree(g_splitk_ws);
+      g_splitk_ws = nullptr;
+      g_splitk_ws_bytes = 0;
+      B200Q_CUDA(cudaMalloc(&g_splitk_ws, need));
+      g_splitk_ws_bytes = need;
+    }
+    ws = g_splitk_ws;
+  }
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K, g_gemm_debug, splits, ws);
   B200Q_LAUNCH_CHECK();
+  if (splits > 1) {
+    const long long mn8 = (long long)M * N / 8;
+    const int rgrid = (int)((mn8 + 255) / 256 < 148 * 8 ? (mn8 + 255) / 256 : 148 * 8);
+    splitk_reduce_kernel<<<rgrid, 256, 0, st>>>((const float4*)ws, (uint4*)C, mn8, splits);
+    B200Q_LAUNCH_CHECK();
+  }
   return B200Q_OK;
 }
 
@@ -720,10 +784,12 @@ static bool prefer_2cta(int M, int N) {
   const long long sms = num_sms(), pairs = sms / 2;
   const long long t2 = (long long)((M + 255) / 256) * (N / 256);
   const long long t1 = (long long)((M + GEMM_BM - 1) / GEMM_BM) * (N / 256);
+  if (t2 < pairs) return false;  // not even one full round of pairs: finer 1-CTA tiles / split-K fill the chip better
   return (t2 + pairs - 1) / pairs <= (t1 + sms - 1) / sms;
 }
 
 int g_gemm_force_bn = 0;  // test hook: 0 = heuristic
+int g_gemm_splitk = 0;    // 0 = auto, 1 = never, n > 1 = force n splits where legal (tests)
 int g_gemm_mode = 0;      // 0 = auto, 1 = force 1-CTA kernels, 2 = force the 2-CTA kernel
 
 }  // namespace b200q
@@ -749,6 +815,13 @@ int b200q_gemm_set_debug(int flags) {
   return B200Q_OK;
 }
 
+// test/tuning hook: 0 = auto split-K, 1 = off, n > 1 = force n splits (decode-sized M only)
+int b200q_gemm_set_splitk(int n) {
+  B200Q_CHECK_ARG(n >= 0 && n <= 16, "split-K factor must be in [0,16]");
+  g_gemm_splitk = n;
+  return B200Q_OK;
+}
+
 int b200q_gemm_set_mode(int mode) {
   B200Q_CHECK_ARG(mode >= 0 && mode <= 2, "gemm mode must be 0/1/2");
   g_gemm_mode = mode;
@@ -770,6 +843,24 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
     if ((bn == 0 || bn == 128) && N % 128 == 0) return launch_gemm2<128>(A, W, C, M, N, K, st);
   }
   if (g_gemm_mode == 0 && bn == 0 && prefer_2cta(M, N)) return launch_gemm2<256>(A, W, C, M, N, K, st);
+  {
+    // split-K for decode-sized batches: when a projection has too few 128-wide output tiles to
+    // put every SM on the weight stream, split the reduction so that tiles x splits ~ #SMs
+    const int want = g_gemm_splitk;  // 0 = auto, 1 = off, >1 = forced (tests)
+    if (want != 1 && bn == 0 && M <= 256 && N % 128 == 0 && N <= 8192) {
+      const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / 128);
+      const int kb = K / GEMM_BK;
+      int splits = want > 1 ? want : 1;
+      if (want == 0 && tiles * 2 <= num_sms()) {
+        for (int sN = 8; sN >= 2; --sN)
+          if (kb % sN == 0 && kb / sN >= 8 && tiles * sN <= num_sms() + num_sms() / 8) {
+            splits = sN;
+            break;
+          }
+      }
+      if (splits > 1 && kb % splits == 0) return launch_gemm<128>(A, W, C, M, N, K, st, splits);
+    }
+  }
   if (bn == 0) {
     // Every CTA walks ceil(tiles / SMs) tiles; measured on B200 (profiles/r1_microbench.md) a
     // 128-wide tile costs ~0.85x and a 64-wide tile ~0.8x the time of a 256-wide one (the kernel

@@ -149,6 +149,7 @@ EXTRA_SIGNATURES = {
     "b200q_gemm_resident_pairs": (_i, []),
     "b200q_gemm_set_debug": (_i, [_i]),
     "b200q_decode_attn_set_variant": (_i, [_i]),
+    "b200q_gemm_set_splitk": (_i, [_i]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -276,3 +276,28 @@ def test_decode_attn_streaming_variant(cuda, D, n_q, n_kv, variant):
         q = qkv[i].float().view(n_q + 2 * n_kv, D)[:n_q][None]
         ref = O.attention(q, ks[i].float(), vs[i].float(), torch.tensor([c - 1]), scale)[0]
         bf16_close(got[i], ref, ulps=2.0, atol=5e-3, max_mismatch_frac=0.5, what=f"decode-stream v{variant} ctx={c}")
+
+
+@pytest.mark.parametrize("splits", [0, 2, 4, 7, 8])
+@pytest.mark.parametrize("M,N,K", [(1, 4096, 4096), (64, 4096, 14336), (130, 6144, 4096), (256, 4096, 14336)])
+def test_gemm_splitk(cuda, M, N, K, splits):
+    """split-K for decode-sized M: fp32 partial tiles + fixed-order reduce == the unsplit result up to
+    fp32 summation order, and bit-identical from run to run"""
+    from llmq_b200 import lib
+    if splits and (K // 64) % splits:
+        pytest.skip("split does not divide the k-blocks")
+    a, w = rnd(M, K, seed=40), rnd(N, K, seed=41, scale=0.05)
+    ad, wd = a.to(cuda), w.to(cuda)
+    c1 = torch.full((M, N), float("nan"), dtype=BF, device=cuda)
+    c2 = torch.full((M, N), float("nan"), dtype=BF, device=cuda)
+    L = lib.load()
+    lib.check(L.b200q_gemm_set_splitk(splits))
+    try:
+        lib.gemm_bf16(ad, wd, c1)
+        lib.gemm_bf16(ad, wd, c2)
+        torch.cuda.synchronize()
+    finally:
+        lib.check(L.b200q_gemm_set_splitk(0))
+    assert torch.equal(c1, c2), "split-K must be deterministic"
+    ref = (ad.float() @ wd.float().t()).to(BF)
+    bf16_close(c1, ref.cpu(), ulps=1.0, atol=2e-5 * math.sqrt(K), max_mismatch_frac=0.02, what=f"splitk={splits} {M}x{N}x{K}")

@@ -187,6 +187,32 @@ def decode_variants(f):
         del kv
 
 
+def gemm_small_m(f):
+    """decode-sized M: split-K (auto) vs no split vs cuBLAS; weight stream GB/s is the figure of merit"""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    shapes = {"qkv": (6144, 4096), "o": (4096, 4096), "down": (4096, 14336)}
+    L = lib.load()
+    for M in (16, 64, 128, 256):
+        for name, (N, K) in shapes.items():
+            a = torch.randn(M, K, device=dev).to(BF)
+            w = (torch.randn(N, K, device=dev) * 0.02).to(BF)
+            c = torch.empty(M, N, dtype=BF, device=dev)
+            res = dict(kind="gemm_small_m", name=name, M=M, N=N, K=K)
+            for tag, sk in (("auto", 0), ("nosplit", 1), ("s2", 2), ("s4", 4), ("s8", 8)):
+                if sk > 1 and (K // 64) % sk:
+                    continue
+                L.b200q_gemm_set_splitk(sk)
+                med, _ = timeit(lambda: lib.gemm_bf16(a, w, c), iters=15, flush=flush)
+                res[f"us_{tag}"] = round(med * 1e3, 2)
+            L.b200q_gemm_set_splitk(0)
+            medc, _ = timeit(lambda: torch.matmul(a, w.t(), out=c), iters=15, flush=flush)
+            res["us_cublas"] = round(medc * 1e3, 2)
+            res["weight_gbs_auto"] = round(N * K * 2 / res["us_auto"] / 1e3, 1)
+            res["weight_gbs_cublas"] = round(N * K * 2 / res["us_cublas"] / 1e3, 1)
+            emit(f, **res)
+            del a, w, c
+
+
 def gemm_limits(f):
     """where do the GEMM's bubbles come from?  time the kernel with the operand loads and/or the
     epilogue switched off (results are garbage in those modes; timing only)"""
@@ -329,4 +355,4 @@ if __name__ == "__main__":
     tag = os.environ.get("PROBE_TAG", "")
     with open(os.path.join(OUT, f"probe_{mode}{tag}.jsonl"), "w") as f:
         {"gemm_check": gemm_check, "bench": bench, "gemm2_bench": gemm2_bench, "ncu_targets": ncu_targets,
-         "argmax_ties": argmax_ties, "gemm_limits": gemm_limits, "decode_variants": decode_variants}[mode](f)
+         "argmax_ties": argmax_ties, "gemm_limits": gemm_limits, "decode_variants": decode_variants, "gemm_small_m": gemm_small_m}[mode](f)

@@ -301,3 +301,45 @@ def test_gemm_splitk(cuda, M, N, K, splits):
     assert torch.equal(c1, c2), "split-K must be deterministic"
     ref = (ad.float() @ wd.float().t()).to(BF)
     bf16_close(c1, ref.cpu(), ulps=1.0, atol=2e-5 * math.sqrt(K), max_mismatch_frac=0.02, what=f"splitk={splits} {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_decode_attn_long_context(cuda, variant):
+    """contexts beyond 32 pages per warp (block-id register window reloads) up to 5000 tokens"""
+    from llmq_b200 import lib
+    D, n_q, n_kv, BS = 128, 8, 2, 16
+    ctxs = [5000, 2049, 513, 4097, 33]
+    kv, bt, ks, vs = _make_cache(ctxs, n_kv, D, BS, seed=51)
+    B = len(ctxs)
+    qkv = rnd(B, (n_q + 2 * n_kv) * D, seed=52)
+    out = torch.full((B, n_q * D), float("nan"), dtype=BF, device=cuda)
+    scale = 1.0 / math.sqrt(D)
+    L = lib.load()
+    lib.check(L.b200q_decode_attn_set_variant(variant))
+    try:
+        lib.decode_attn(qkv.to(cuda), out, kv.to(cuda), bt.to(cuda),
+                        torch.tensor(ctxs, dtype=torch.int32, device=cuda), n_q, n_kv, D, BS, scale)
+        torch.cuda.synchronize()
+    finally:
+        lib.check(L.b200q_decode_attn_set_variant(0))
+    got = out.float().cpu().view(B, n_q, D)
+    for i, c in enumerate(ctxs):
+        q = qkv[i].float().view(n_q + 2 * n_kv, D)[:n_q][None]
+        ref = O.attention(q, ks[i].float(), vs[i].float(), torch.tensor([c - 1]), scale)[0]
+        bf16_close(got[i], ref, ulps=2.0, atol=5e-3, max_mismatch_frac=0.5, what=f"decode long ctx={c} v{variant}")
+
+
+def test_prefill_attn_long_context_chunk(cuda):
+    """a 40-token chunk appended to a 3000-token context (chunked prefill deep into a sequence)"""
+    from llmq_b200 import lib
+    D, n_q, n_kv, BS = 128, 8, 2, 16
+    a, n = 3000, 40
+    kv, bt, ks, vs = _make_cache([a + n], n_kv, D, BS, seed=53)
+    qkv = rnd(n, (n_q + 2 * n_kv) * D, seed=54)
+    tiles = torch.tensor([[0, j, min(16, n - j), a + j] for j in range(0, n, 16)], dtype=torch.int32)
+    out = torch.zeros(n, n_q * D, dtype=BF, device=cuda)
+    scale = 1.0 / math.sqrt(D)
+    lib.prefill_attn(qkv.to(cuda), out, kv.to(cuda), bt.to(cuda), tiles.to(cuda), n_q, n_kv, D, BS, scale)
+    q = qkv.float().view(n, n_q + 2 * n_kv, D)[:, :n_q]
+    ref = O.attention(q, ks[0].float(), vs[0].float(), torch.arange(a, a + n), scale)
+    bf16_close(out.float().cpu().view(n, n_q, D), ref, ulps=2.0, atol=5e-3, max_mismatch_frac=0.5, what="prefill long ctx")

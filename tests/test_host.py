@@ -145,3 +145,82 @@ def test_job_stream_is_sharding_invariant():
     merged = sorted((j for s in shards for j in s), key=lambda j: j["id"])
     assert merged == full and len({j["id"] for j in full}) == 12
     assert json.loads(json.dumps(full[0]))["prompt"].count("w") == 5
+
+
+def test_config1_dummy_worker_1k_jobs_through_broker(monkeypatch):
+    """BASELINE config #1: the reference's own DummyWorker (unmodified), 1k synthetic JSONL jobs
+    through the broker — plumbing only.  Its 1 s sleep per job is patched to 1 ms."""
+    import llmq.workers.dummy_worker as DW
+    aio_pika.reset_brokers()
+    real_sleep = asyncio.sleep
+
+    async def fast_sleep(t):
+        await real_sleep(0.001 if t == 1.0 else t)
+
+    monkeypatch.setattr(DW.asyncio, "sleep", fast_sleep)
+
+    async def main():
+        w = DW.DummyWorker("dq", concurrency=250)
+        task = asyncio.create_task(w.run())
+        b = BrokerManager()
+        await b.connect()
+        await b.setup_queue_infrastructure("dq")
+        for i in range(1000):
+            await b.publish_job("dq", Job(id=f"job-{i:07d}", prompt="{text}", text=f"t{i}"))
+        got = {}
+
+        async def on_res(m):
+            r = Result.parse_raw(m.body)
+            got[r.id] = r.result
+            await m.ack()
+
+        await b.consume_results("dq", on_res)
+        for _ in range(400):
+            if len(got) >= 1000:
+                break
+            await real_sleep(0.05)
+        w.running = False
+        await asyncio.wait_for(task, 10)
+        return got
+
+    got = asyncio.run(main())
+    assert len(got) == 1000 and got["job-0000042"] == "echo t42"
+
+
+def test_pipeline_stage_routing_with_native_worker(patched):
+    """config #4 plumbing: two B200Worker stages of a pipeline; stage 1's result becomes stage 2's
+    prompt through the reference's publish_pipeline_result (ref:llmq/core/broker.py:145-193)"""
+    made, tok = patched
+
+    async def main():
+        stages = ["translate", "format"]
+        w1 = B200Worker("m", "pipeline.p.translate", pipeline_name="p", stage_name="translate", pipeline_stages=stages)
+        w2 = B200Worker("m", "pipeline.p.format", pipeline_name="p", stage_name="format", pipeline_stages=stages)
+        t1, t2 = asyncio.create_task(w1.run()), asyncio.create_task(w2.run())
+        b = BrokerManager()
+        await b.connect()
+        await b.setup_pipeline_infrastructure("p", stages)
+        for i in range(5):
+            await b.publish_job("pipeline.p.translate", Job(id=f"p{i}", prompt=f"w{100 + i}", src=f"s{i}", temperature=0))
+        got = {}
+
+        async def on_res(m):
+            r = Result.parse_raw(m.body)
+            got[r.id] = r
+            await m.ack()
+
+        await b.consume_results("pipeline.p.results", on_res)
+        for _ in range(200):
+            if len(got) >= 5:
+                break
+            await asyncio.sleep(0.05)
+        w1.running = w2.running = False
+        await asyncio.wait_for(asyncio.gather(t1, t2), 10)
+        return got
+
+    got = asyncio.run(main())
+    assert len(got) == 5
+    # stage 1 counts up from w100: "w101 .. w106"; stage 2 is prompted with that text and counts up
+    # from its last token w106: "w107 .. w112"; extras ride along
+    assert got["p0"].result == "w107 w108 w109 w110 w111 w112"
+    assert got["p0"].prompt == "w101 w102 w103 w104 w105 w106" and got["p0"].model_dump()["src"] == "s0"

@@ -16,6 +16,7 @@
 // Roofline: decode-sized M is HBM-bound on the weight stream (N*K*2 bytes), M >= ~256 is
 // tensor-bound (2*M*N*K flops against the measured bf16 peak).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -846,7 +847,14 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
   {
     // split-K for decode-sized batches: when a projection has too few 128-wide output tiles to
     // put every SM on the weight stream, split the reduction so that tiles x splits ~ #SMs
-    const int want = g_gemm_splitk;  // 0 = auto, 1 = off, >1 = forced (tests)
+    // B200Q_BATCH_INVARIANT=1 (read once): never split K, so every output element is reduced in
+    // one sequential pass and a request's tokens cannot depend on its batch-mates (like
+    // VLLM_BATCH_INVARIANT); costs decode-sized GEMMs up to 2x
+    static const bool env_invariant = [] {
+      const char* v = getenv("B200Q_BATCH_INVARIANT");
+      return v && v[0] == '1';
+    }();
+    const int want = env_invariant ? 1 : g_gemm_splitk;  // 0 = auto, 1 = off, >1 = forced (tests)
     if (want != 1 && bn == 0 && M <= 256 && N % 128 == 0 && N <= 8192) {
       const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / 128);
       const int kb = K / GEMM_BK;

@@ -13,6 +13,7 @@
 // int32 metadata (token ids, positions, slot mapping, context lengths, prefill q-tiles, sample
 // rows, block table), ships it with one H2D copy, runs the forward on the engine's stream and
 // reads back the sampled ids with one D2H copy.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -25,6 +26,7 @@
 namespace b200q {
 const b200q_model_config& model_cfg(b200q_model_t m);
 int64_t model_num_blocks(b200q_model_t m);
+bool model_is_profiling(b200q_model_t m);
 }  // namespace b200q
 
 using namespace b200q;
@@ -69,6 +71,16 @@ struct b200q_engine {
   int32_t* d_out = nullptr;
 
   b200q_engine_stats stats{};
+
+  // CUDA graphs of the forward for decode-only steps, keyed by (tokens, block-table stride,
+  // sampled?) — every device pointer in the batch is a fixed function of that key.  Removes the
+  // ~330 launch gaps per step, which is what small decode batches are bound by.
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+  };
+  std::unordered_map<uint64_t, GraphEntry> graphs;
+  bool use_graphs = true;
 };
 
 static void free_request_blocks(b200q_engine* e, Request* r) {
@@ -128,6 +140,10 @@ int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b20
     b200q_engine_destroy(e);
     return B200Q_ECUDA;
   }
+  {
+    const char* v = getenv("B200Q_CUDA_GRAPHS");
+    e->use_graphs = !(v && v[0] == '0');
+  }
   // weights / KV were produced on other streams (torch); make them visible before first use
   cudaDeviceSynchronize();
   *out = e;
@@ -137,6 +153,7 @@ int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b20
 int b200q_engine_destroy(b200q_engine_t e) {
   if (!e) return B200Q_OK;
   if (e->stream) cudaStreamSynchronize(e->stream);
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (auto& kv : e->by_id) delete kv.second;
   if (e->h_meta) cudaFreeHost(e->h_meta);
   if (e->d_meta) cudaFree(e->d_meta);
@@ -421,7 +438,50 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
           (int64_t)(4.0 * pairs * e->mcfg.n_q_heads * e->mcfg.head_dim);
     }
   }
-  int rc = b200q_model_forward(e->model, &b, e->stream);
+  int rc = B200Q_OK;
+  bool launched = false;
+  if (e->use_graphs && n_tiles == 0 && T == n_dec && !model_is_profiling(e->model) &&
+      e->stats.steps >= 2 /* first steps run eagerly: one-time attribute/occupancy/scratch setup */) {
+    const uint64_t key = (uint64_t)T | ((uint64_t)bt_stride << 16) | ((uint64_t)(any_sampled ? 1 : 0) << 32);
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+      const int64_t l0 = b200q_launch_count();
+      cudaGraph_t g = nullptr;
+      b200q_engine::GraphEntry ge;
+      if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        rc = b200q_model_forward(e->model, &b, e->stream);
+        cudaError_t ee = cudaStreamEndCapture(e->stream, &g);
+        if (rc == B200Q_OK && ee == cudaSuccess && g &&
+            cudaGraphInstantiate(&ge.exec, g, 0) == cudaSuccess) {
+          ge.launches = b200q_launch_count() - l0;
+          if (e->graphs.size() > 512) {  // bounded cache
+            for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+            e->graphs.clear();
+          }
+          it = e->graphs.emplace(key, ge).first;
+        } else {
+          cudaGetLastError();
+          e->use_graphs = false;  // fall back to eager launches for good
+          rc = B200Q_OK;
+        }
+        if (g) cudaGraphDestroy(g);
+      } else {
+        cudaGetLastError();
+        e->use_graphs = false;
+      }
+    } else {
+      count_launch((int)it->second.launches);  // the replay runs the same kernels again
+    }
+    if (it != e->graphs.end() && e->use_graphs) {
+      if (cudaGraphLaunch(it->second.exec, e->stream) == cudaSuccess) {
+        launched = true;
+      } else {
+        cudaGetLastError();
+        e->use_graphs = false;
+      }
+    }
+  }
+  if (!launched) rc = b200q_model_forward(e->model, &b, e->stream);
   if (rc) return rc;
   if (n_sample > 0) {
     ce = cudaMemcpyAsync(e->h_out, e->d_out, (size_t)n_sample * 4, cudaMemcpyDeviceToHost, e->stream);

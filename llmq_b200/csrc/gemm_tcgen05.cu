@@ -706,13 +706,14 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
   const int grid = tiles < num_sms() ? tiles : num_sms();
   float* ws = nullptr;
   if (splits > 1) {
+    // fixed-size scratch (8 splits x 256 rows x 8192 cols fp32 = 64 MiB), allocated once and never
+    // moved: CUDA graphs captured by the engine bake this pointer into their kernel nodes
     const size_t need = (size_t)splits * M * N * sizeof(float);
-    if (need > g_splitk_ws_bytes) {  // grow-only scratch owned by the library
-      if (g_splitk_ws) cudaFree(g_splitk_ws);
-      g_splitk_ws = nullptr;
-      g_splitk_ws_bytes = 0;
-      B200Q_CUDA(cudaMalloc(&g_splitk_ws, need));
-      g_splitk_ws_bytes = need;
+    const size_t cap = (size_t)8 * 256 * 8192 * sizeof(float);
+    B200Q_CHECK_ARG(need <= cap, "split-K scratch too small for M=%d N=%d splits=%d", M, N, splits);
+    if (!g_splitk_ws) {
+      B200Q_CUDA(cudaMalloc(&g_splitk_ws, cap));
+      g_splitk_ws_bytes = cap;
     }
     ws = g_splitk_ws;
   }
@@ -866,7 +867,7 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
             break;
           }
       }
-      if (splits > 1 && kb % splits == 0) return launch_gemm<128>(A, W, C, M, N, K, st, splits);
+      if (splits > 1 && splits <= 8 && kb % splits == 0) return launch_gemm<128>(A, W, C, M, N, K, st, splits);
     }
   }
   if (bn == 0) {

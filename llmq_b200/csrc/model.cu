@@ -317,4 +317,5 @@ int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
 namespace b200q {
 const b200q_model_config& model_cfg(b200q_model_t m) { return m->cfg; }
 int64_t model_num_blocks(b200q_model_t m) { return m->num_blocks; }
+bool model_is_profiling(b200q_model_t m) { return m->profiling; }
 }  // namespace b200q

@@ -243,3 +243,27 @@ def test_engine_sampling_is_seeded_and_batch_invariant(cuda):
     assert greedy[2] == a[2]
     assert a[0] != greedy[0] or a[1] != greedy[1] or a[3] != greedy[3], "sampling never differed from greedy"
     model.close()
+
+
+def test_engine_cuda_graph_replay_equals_eager(cuda, monkeypatch):
+    """decode-only steps are replayed from CUDA graphs; tokens must equal the eager engine's"""
+    from llmq_b200.model import Engine
+    dims = TINY["d128"]
+    model, oracle, _ = build(dims)
+    reqs = prompts(dims.vocab, [30, 31, 9, 64, 17, 40], seed=77)
+
+    def run(graphs):
+        monkeypatch.setenv("B200Q_CUDA_GRAPHS", "1" if graphs else "0")
+        eng = Engine(model, max_num_seqs=8, max_num_batched_tokens=256, eos_token_id=None)
+        for i, p in enumerate(reqs):
+            eng.add_request(i, p, 40, ignore_eos=True, temperature=0.7 if i % 2 else 0.0, seed=100 + i)
+        outs = {i: [] for i in range(len(reqs))}
+        while eng.has_work():
+            ids, toks, _ = eng.step()
+            for i, t in zip(ids.tolist(), toks.tolist()):
+                outs[i].append(t)
+        eng.close()
+        return outs
+
+    assert run(True) == run(False)
+    model.close()

@@ -702,6 +702,7 @@ extern "C" {
 int b200q_decode_attn_set_variant(int v) {
   B200Q_CHECK_ARG(v >= 0 && v <= 3, "decode variant must be 0..3");
   g_decode_variant = v;
+  bump_tuning_epoch();
   return B200Q_OK;
 }
 

@@ -13,6 +13,9 @@ namespace b200q {
 void set_error(const char* fmt, ...);
 extern thread_local char g_err[512];
 void count_launch(int n = 1);
+// bumped by every test/tuning setter: cached CUDA graphs bake kernel choices in and must be rebuilt
+void bump_tuning_epoch();
+int tuning_epoch();
 
 #define B200Q_CHECK_ARG(cond, ...)          \
   do {                                      \

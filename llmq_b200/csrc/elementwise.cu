@@ -19,6 +19,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
+static int g_epoch = 0;
+void bump_tuning_epoch() { __atomic_fetch_add(&g_epoch, 1, __ATOMIC_RELAXED); }
+int tuning_epoch() { return __atomic_load_n(&g_epoch, __ATOMIC_RELAXED); }
 
 // ------------------------------------------------------------------------------------------
 // K1 embedding gather.  One warp per 512 B (32 lanes x 16 B); grid-stride over (token, chunk).

@@ -80,6 +80,7 @@ struct b200q_engine {
     int64_t launches = 0;
   };
   std::unordered_map<uint64_t, GraphEntry> graphs;
+  int graph_epoch = 0;  // tuning_epoch() the cached graphs were captured under
   bool use_graphs = true;
 };
 
@@ -442,6 +443,11 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
   bool launched = false;
   if (e->use_graphs && n_tiles == 0 && T == n_dec && !model_is_profiling(e->model) &&
       e->stats.steps >= 2 /* first steps run eagerly: one-time attribute/occupancy/scratch setup */) {
+    if (e->graph_epoch != tuning_epoch()) {  // a tuning hook changed kernel selection: rebuild
+      for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+      e->graphs.clear();
+      e->graph_epoch = tuning_epoch();
+    }
     const uint64_t key = (uint64_t)T | ((uint64_t)bt_stride << 16) | ((uint64_t)(any_sampled ? 1 : 0) << 32);
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {

@@ -804,6 +804,7 @@ extern "C" {
 int b200q_gemm_set_tile_n(int bn) {
   B200Q_CHECK_ARG(bn == 0 || bn == 64 || bn == 128 || bn == 256, "gemm tile N must be 0/64/128/256");
   g_gemm_force_bn = bn;
+  bump_tuning_epoch();
   return B200Q_OK;
 }
 
@@ -814,6 +815,7 @@ int b200q_gemm_resident_pairs(void) { return g_gemm2_pairs; }
 // timing experiments only — results are garbage: bit0 skips the operand loads, bit1 the epilogue
 int b200q_gemm_set_debug(int flags) {
   g_gemm_debug = flags & 3;
+  bump_tuning_epoch();
   return B200Q_OK;
 }
 
@@ -821,12 +823,14 @@ int b200q_gemm_set_debug(int flags) {
 int b200q_gemm_set_splitk(int n) {
   B200Q_CHECK_ARG(n >= 0 && n <= 16, "split-K factor must be in [0,16]");
   g_gemm_splitk = n;
+  bump_tuning_epoch();
   return B200Q_OK;
 }
 
 int b200q_gemm_set_mode(int mode) {
   B200Q_CHECK_ARG(mode >= 0 && mode <= 2, "gemm mode must be 0/1/2");
   g_gemm_mode = mode;
+  bump_tuning_epoch();
   return B200Q_OK;
 }
 

@@ -81,6 +81,7 @@ struct b200q_engine {
   };
   std::unordered_map<uint64_t, GraphEntry> graphs;
   int graph_epoch = 0;  // tuning_epoch() the cached graphs were captured under
+  bool admitting = false;  // admission hysteresis state (policy 1)
   bool use_graphs = true;
 };
 
@@ -319,7 +320,19 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     admit_waiting();
   } else {
     schedule_running(1);
-    admit_waiting();
+    // admission hysteresis: under a steady backlog a slot frees up almost every step, and
+    // admitting one prompt at a time would put a tiny prefill chunk into every step (no step is
+    // decode-only => no CUDA-graph replay, prefill GEMMs at M ~ 128).  Wait until a batch of
+    // slots (1/16 of max_num_seqs) is free, then admit until the slots or the budget run out.
+    const int free_slots = e->cfg.max_num_seqs - (int)e->running.size();
+    const int thresh = std::max(1, e->cfg.max_num_seqs / 16);
+    const bool mid_prefill = !sched.empty();  // an unfinished prompt is in flight: keep the phase going
+    if (e->running.empty() || mid_prefill || free_slots >= thresh || e->admitting) {
+      const size_t before = e->running.size();
+      admit_waiting();
+      e->admitting = e->running.size() > before && !e->waiting.empty() &&
+                     (int)e->running.size() < e->cfg.max_num_seqs;
+    }
     schedule_running(2);
   }
 

@@ -260,6 +260,8 @@ def run_native(args):
     torch.cuda.set_device(local)
     L.require_device()
     dist = None
+    if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL's version banner goes there)
     if world > 1:
         import torch.distributed as dist_mod
 

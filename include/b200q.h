@@ -242,6 +242,12 @@ typedef struct b200q_engine_stats {
 } b200q_engine_stats;
 
 int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b200q_engine_t* out);
+/* Scheduler self-test engine (host-logic tests on machines without a GPU): no model, no CUDA.
+ * step() builds the per-step metadata exactly as in production, checks its invariants (budget,
+ * unique KV slots, tile cover, positions) and fabricates each "sampled" token as
+ * (previous token + 1) mod vocab.  It cannot run a model and is never used by the worker. */
+int b200q_engine_create_dryrun(const b200q_engine_config* cfg, int32_t vocab, int32_t block_size,
+                               int32_t num_blocks, b200q_engine_t* out);
 int b200q_engine_destroy(b200q_engine_t e);
 /* prompt ids are copied.  Returns B200Q_EINVAL if n_prompt + 1 > max_model_len (the worker
  * turns that into ValueError => job dropped, ref:llmq/workers/base.py:228-235). */

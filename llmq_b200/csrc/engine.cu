@@ -82,6 +82,10 @@ struct b200q_engine {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   int graph_epoch = 0;  // tuning_epoch() the cached graphs were captured under
   bool admitting = false;  // admission hysteresis state (policy 1)
+  // scheduler self-test mode (b200q_engine_create_dryrun): no model, no CUDA — step() builds the
+  // batch metadata exactly as in production, checks its invariants and fabricates the "sampled"
+  // token as (previous token + 1) mod vocab.  Host-logic tests only; never reachable from the worker.
+  bool dry_run = false;
   bool use_graphs = true;
 };
 
@@ -152,8 +156,48 @@ int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b20
   return B200Q_OK;
 }
 
+int b200q_engine_create_dryrun(const b200q_engine_config* cfg, int32_t vocab, int32_t block_size,
+                               int32_t num_blocks, b200q_engine_t* out) {
+  B200Q_CHECK_ARG(cfg && out && vocab > 1 && block_size > 0 && num_blocks > 0, "create_dryrun: bad argument");
+  B200Q_CHECK_ARG(cfg->max_num_seqs > 0 && cfg->max_num_batched_tokens > 0 && cfg->max_model_len > 1,
+                  "create_dryrun: bad engine config");
+  b200q_engine* e = new b200q_engine();
+  e->dry_run = true;
+  e->use_graphs = false;
+  e->model = nullptr;
+  e->cfg = *cfg;
+  memset(&e->mcfg, 0, sizeof(e->mcfg));
+  e->mcfg.vocab = vocab;
+  e->mcfg.block_size = block_size;
+  e->mcfg.n_q_heads = 1;
+  e->mcfg.head_dim = 1;
+  e->block_size = block_size;
+  e->max_blocks_per_seq = (cfg->max_model_len + block_size - 1) / block_size;
+  e->total_blocks = num_blocks;
+  for (int32_t b = num_blocks - 1; b >= 0; --b) e->free_blocks.push_back(b);
+  const int64_t T = cfg->max_num_batched_tokens, S = cfg->max_num_seqs;
+  e->meta_cap = 3 * T + 2 * S + 4 * S + 8 + 4 * (T / 16 + S + 2) +
+                S * (int64_t)((e->max_blocks_per_seq + 7) & ~7) + 64;
+  e->h_meta = (int32_t*)malloc(e->meta_cap * 4);
+  e->h_out = (int32_t*)malloc(S * 4);
+  if (!e->h_meta || !e->h_out) {
+    set_error("create_dryrun: out of host memory");
+    b200q_engine_destroy(e);
+    return B200Q_ENOMEM;
+  }
+  *out = e;
+  return B200Q_OK;
+}
+
 int b200q_engine_destroy(b200q_engine_t e) {
   if (!e) return B200Q_OK;
+  if (e->dry_run) {
+    for (auto& kv : e->by_id) delete kv.second;
+    free(e->h_meta);
+    free(e->h_out);
+    delete e;
+    return B200Q_OK;
+  }
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (auto& kv : e->by_id) delete kv.second;
@@ -419,100 +463,130 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     row += r->n_sched;
   }
 
-  cudaError_t ce = cudaMemcpyAsync(e->d_meta, e->h_meta, used * 4, cudaMemcpyHostToDevice, e->stream);
-  if (ce != cudaSuccess) {
-    set_error("step: H2D metadata copy failed: %s", cudaGetErrorString(ce));
-    return B200Q_ECUDA;
-  }
-  b200q_batch b;
-  b.T = T;
-  b.n_dec = n_dec;
-  b.n_tiles = n_tiles;
-  b.n_sample = n_sample;
-  b.bt_stride = bt_stride;
-  b.token_ids = e->d_meta + (tok - e->h_meta);
-  b.positions = e->d_meta + (pos - e->h_meta);
-  b.slot_mapping = e->d_meta + (slot - e->h_meta);
-  b.ctx_lens = e->d_meta + (ctx - e->h_meta);
-  b.sample_rows = e->d_meta + (srows - e->h_meta);
-  b.tiles = e->d_meta + (tiles - e->h_meta);
-  b.block_table = e->d_meta + (btab - e->h_meta);
-  b.out_ids = e->d_out;
-  b.sample_params = any_sampled ? e->d_meta + (sparams - e->h_meta) : nullptr;
-  b.sum_ctx_dec = 0;
-  b.prefill_flops_per_layer = 0;
-  for (Request* r : sched) {
-    if (r->n_sched == 1) {
-      b.sum_ctx_dec += r->n_computed + 1;
-    } else {
-      // causal: query j of the chunk sees n_computed + j + 1 keys; QK^T and PV, 2 flops per MAC
-      const double q = r->n_sched, c0 = r->n_computed;
-      const double pairs = q * c0 + q * (q + 1) / 2;
-      b.prefill_flops_per_layer +=
-          (int64_t)(4.0 * pairs * e->mcfg.n_q_heads * e->mcfg.head_dim);
+  if (e->dry_run) {
+    // ---- invariants of the metadata the kernels would consume ----
+    int rc = B200Q_OK;
+    auto fail = [&](const char* what) {
+      set_error("scheduler self-test: %s (T=%d n_dec=%d n_tiles=%d)", what, T, n_dec, n_tiles);
+      rc = B200Q_ESTATE;
+    };
+    if (T > e->cfg.max_num_batched_tokens) fail("token budget exceeded");
+    if (n_rows > e->cfg.max_num_seqs) fail("more sequences than max_num_seqs");
+    std::vector<char> slot_seen((size_t)e->total_blocks * e->block_size, 0);
+    for (int t = 0; t < T && rc == B200Q_OK; ++t) {
+      if (slot[t] < 0 || slot[t] >= (int)slot_seen.size()) fail("slot out of range");
+      else if (slot_seen[slot[t]]++) fail("two tokens of one step share a KV slot");
+      if (tok[t] < 0 || tok[t] >= e->mcfg.vocab) fail("token id out of range");
     }
-  }
-  int rc = B200Q_OK;
-  bool launched = false;
-  if (e->use_graphs && n_tiles == 0 && T == n_dec && !model_is_profiling(e->model) &&
-      e->stats.steps >= 2 /* first steps run eagerly: one-time attribute/occupancy/scratch setup */) {
-    if (e->graph_epoch != tuning_epoch()) {  // a tuning hook changed kernel selection: rebuild
-      for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
-      e->graphs.clear();
-      e->graph_epoch = tuning_epoch();
+    int covered = n_dec;
+    for (int i = 0; i < n_tiles && rc == B200Q_OK; ++i) {
+      const int32_t* tl = tiles + 4 * i;
+      if (tl[1] != covered || tl[2] < 1 || tl[2] > 16 || tl[0] < n_dec || tl[0] >= n_rows) fail("bad prefill tile");
+      else if (pos[tl[1]] != tl[3]) fail("tile position does not match its first token");
+      covered += tl[2];
     }
-    const uint64_t key = (uint64_t)T | ((uint64_t)bt_stride << 16) | ((uint64_t)(any_sampled ? 1 : 0) << 32);
-    auto it = e->graphs.find(key);
-    if (it == e->graphs.end()) {
-      const int64_t l0 = b200q_launch_count();
-      cudaGraph_t g = nullptr;
-      b200q_engine::GraphEntry ge;
-      if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
-        rc = b200q_model_forward(e->model, &b, e->stream);
-        cudaError_t ee = cudaStreamEndCapture(e->stream, &g);
-        if (rc == B200Q_OK && ee == cudaSuccess && g &&
-            cudaGraphInstantiate(&ge.exec, g, 0) == cudaSuccess) {
-          ge.launches = b200q_launch_count() - l0;
-          if (e->graphs.size() > 512) {  // bounded cache
-            for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
-            e->graphs.clear();
-          }
-          it = e->graphs.emplace(key, ge).first;
-        } else {
-          cudaGetLastError();
-          e->use_graphs = false;  // fall back to eager launches for good
-          rc = B200Q_OK;
-        }
-        if (g) cudaGraphDestroy(g);
-      } else {
-        cudaGetLastError();
-        e->use_graphs = false;
-      }
-    } else {
-      count_launch((int)it->second.launches);  // the replay runs the same kernels again
-    }
-    if (it != e->graphs.end() && e->use_graphs) {
-      if (cudaGraphLaunch(it->second.exec, e->stream) == cudaSuccess) {
-        launched = true;
-      } else {
-        cudaGetLastError();
-        e->use_graphs = false;
-      }
-    }
-  }
-  if (!launched) rc = b200q_model_forward(e->model, &b, e->stream);
-  if (rc) return rc;
-  if (n_sample > 0) {
-    ce = cudaMemcpyAsync(e->h_out, e->d_out, (size_t)n_sample * 4, cudaMemcpyDeviceToHost, e->stream);
+    if (rc == B200Q_OK && covered != T) fail("prefill tiles do not cover the prefill rows exactly");
+    for (int ri = 0; ri < n_dec && rc == B200Q_OK; ++ri)
+      if (ctx[ri] != pos[ri] + 1) fail("decode context length != position + 1");
+    if (rc) return rc;
+    for (Request* r : sched)
+      if (r->sample_slot >= 0) e->h_out[r->sample_slot] = (r->tokens.back() + 1) % e->mcfg.vocab;
+  } else {
+    cudaError_t ce = cudaMemcpyAsync(e->d_meta, e->h_meta, used * 4, cudaMemcpyHostToDevice, e->stream);
     if (ce != cudaSuccess) {
-      set_error("step: D2H copy failed: %s", cudaGetErrorString(ce));
+      set_error("step: H2D metadata copy failed: %s", cudaGetErrorString(ce));
       return B200Q_ECUDA;
     }
-  }
-  ce = cudaStreamSynchronize(e->stream);
-  if (ce != cudaSuccess) {
-    set_error("step: forward failed: %s", cudaGetErrorString(ce));
-    return B200Q_ECUDA;
+    b200q_batch b;
+    b.T = T;
+    b.n_dec = n_dec;
+    b.n_tiles = n_tiles;
+    b.n_sample = n_sample;
+    b.bt_stride = bt_stride;
+    b.token_ids = e->d_meta + (tok - e->h_meta);
+    b.positions = e->d_meta + (pos - e->h_meta);
+    b.slot_mapping = e->d_meta + (slot - e->h_meta);
+    b.ctx_lens = e->d_meta + (ctx - e->h_meta);
+    b.sample_rows = e->d_meta + (srows - e->h_meta);
+    b.tiles = e->d_meta + (tiles - e->h_meta);
+    b.block_table = e->d_meta + (btab - e->h_meta);
+    b.out_ids = e->d_out;
+    b.sample_params = any_sampled ? e->d_meta + (sparams - e->h_meta) : nullptr;
+    b.sum_ctx_dec = 0;
+    b.prefill_flops_per_layer = 0;
+    for (Request* r : sched) {
+      if (r->n_sched == 1) {
+        b.sum_ctx_dec += r->n_computed + 1;
+      } else {
+        // causal: query j of the chunk sees n_computed + j + 1 keys; QK^T and PV, 2 flops per MAC
+        const double q = r->n_sched, c0 = r->n_computed;
+        const double pairs = q * c0 + q * (q + 1) / 2;
+        b.prefill_flops_per_layer +=
+            (int64_t)(4.0 * pairs * e->mcfg.n_q_heads * e->mcfg.head_dim);
+      }
+    }
+    int rc = B200Q_OK;
+    bool launched = false;
+    if (e->use_graphs && n_tiles == 0 && T == n_dec && !model_is_profiling(e->model) &&
+        e->stats.steps >= 2 /* first steps run eagerly: one-time attribute/occupancy/scratch setup */) {
+      if (e->graph_epoch != tuning_epoch()) {  // a tuning hook changed kernel selection: rebuild
+        for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+        e->graphs.clear();
+        e->graph_epoch = tuning_epoch();
+      }
+      const uint64_t key = (uint64_t)T | ((uint64_t)bt_stride << 16) | ((uint64_t)(any_sampled ? 1 : 0) << 32);
+      auto it = e->graphs.find(key);
+      if (it == e->graphs.end()) {
+        const int64_t l0 = b200q_launch_count();
+        cudaGraph_t g = nullptr;
+        b200q_engine::GraphEntry ge;
+        if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+          rc = b200q_model_forward(e->model, &b, e->stream);
+          cudaError_t ee = cudaStreamEndCapture(e->stream, &g);
+          if (rc == B200Q_OK && ee == cudaSuccess && g &&
+              cudaGraphInstantiate(&ge.exec, g, 0) == cudaSuccess) {
+            ge.launches = b200q_launch_count() - l0;
+            if (e->graphs.size() > 512) {  // bounded cache
+              for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
+              e->graphs.clear();
+            }
+            it = e->graphs.emplace(key, ge).first;
+          } else {
+            cudaGetLastError();
+            e->use_graphs = false;  // fall back to eager launches for good
+            rc = B200Q_OK;
+          }
+          if (g) cudaGraphDestroy(g);
+        } else {
+          cudaGetLastError();
+          e->use_graphs = false;
+        }
+      } else {
+        count_launch((int)it->second.launches);  // the replay runs the same kernels again
+      }
+      if (it != e->graphs.end() && e->use_graphs) {
+        if (cudaGraphLaunch(it->second.exec, e->stream) == cudaSuccess) {
+          launched = true;
+        } else {
+          cudaGetLastError();
+          e->use_graphs = false;
+        }
+      }
+    }
+    if (!launched) rc = b200q_model_forward(e->model, &b, e->stream);
+    if (rc) return rc;
+    if (n_sample > 0) {
+      ce = cudaMemcpyAsync(e->h_out, e->d_out, (size_t)n_sample * 4, cudaMemcpyDeviceToHost, e->stream);
+      if (ce != cudaSuccess) {
+        set_error("step: D2H copy failed: %s", cudaGetErrorString(ce));
+        return B200Q_ECUDA;
+      }
+    }
+    ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) {
+      set_error("step: forward failed: %s", cudaGetErrorString(ce));
+      return B200Q_ECUDA;
+    }
   }
 
   // ---- 4. update from output ----

@@ -134,6 +134,7 @@ SIGNATURES = {
     "b200q_model_profile_collect": (_i, [_vp, C.POINTER(Profile), _i]),
     "b200q_engine_stream": (_vp, [_vp]),
     "b200q_engine_create": (_i, [_vp, C.POINTER(EngineConfig), C.POINTER(_vp)]),
+    "b200q_engine_create_dryrun": (_i, [C.POINTER(EngineConfig), C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
     "b200q_engine_destroy": (_i, [_vp]),
     "b200q_engine_add_request": (_i, [_vp, _i64, _vp, C.c_int32, C.c_int32, C.c_int32]),
     "b200q_engine_add_request_sampled": (_i, [_vp, _i64, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64]),

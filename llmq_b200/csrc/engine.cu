@@ -346,9 +346,13 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     while (budget > 0 && !e->waiting.empty() && (int)e->running.size() < e->cfg.max_num_seqs) {
       Request* r = e->waiting.front();
       const int n_new = std::min((int)r->tokens.size() - r->n_computed, budget);
-      // watermark: leave the running decodes ~2 steps' worth of fresh blocks, so that an admission
-      // is not immediately undone by a preemption
-      const int need = (r->n_computed + n_new + e->block_size - 1) / e->block_size - (int)r->blocks.size();
+      // admission control: the blocks for the request's WHOLE current sequence (prompt, plus the
+      // generated tokens a preempted request has to recompute) must be free, on top of a watermark of
+      // ~2 steps' worth of fresh blocks for the running decodes.  Admitting on the first chunk alone
+      // lets a request start a prefill it cannot finish: it preempts itself at the last block, is
+      // re-admitted at once (prefill first) and starves the decodes whose completion would have
+      // freed the memory — a livelock found by tests/test_scheduler_dryrun.py.
+      const int need = ((int)r->tokens.size() + e->block_size - 1) / e->block_size - (int)r->blocks.size();
       const int reserve = e->running.empty() ? 0 : (int)e->running.size() / 8 + 1;
       if ((int)e->free_blocks.size() - need < reserve) break;
       if (!ensure_blocks(e, r, r->n_computed + n_new)) break;

@@ -32,8 +32,9 @@ struct b200q_model {
   // workspace views
   uint8_t* ws = nullptr;
   int64_t ws_bytes = 0;
-  bf16 *x = nullptr, *residual = nullptr, *qkv = nullptr, *attn = nullptr, *gate_up = nullptr,
-       *act = nullptr, *sel = nullptr, *logits = nullptr;
+  // (no [T, 2I] gate_up buffer: the SwiGLU is applied in the gate_up GEMM's epilogue)
+  bf16 *x = nullptr, *residual = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr,
+       *sel = nullptr, *logits = nullptr;
   // optional per-category device timing (CUDA events on the forward's stream)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -87,7 +88,6 @@ int64_t b200q_model_workspace_bytes(const b200q_model_config* c) {
   b += 2 * align256(T * c->hidden * 2);                                  // x, residual
   b += align256(T * qkv_dim(*c) * 2);                                    // qkv
   b += align256(T * (int64_t)c->n_q_heads * c->head_dim * 2);            // attn
-  b += align256(T * 2 * (int64_t)c->intermediate * 2);                   // gate_up
   b += align256(T * (int64_t)c->intermediate * 2);                       // act
   b += align256(S * (int64_t)c->hidden * 2);                             // sel
   b += align256(S * (int64_t)c->vocab * 2);                              // logits
@@ -192,7 +192,6 @@ int b200q_model_bind_workspace(b200q_model_t m, void* p, int64_t bytes) {
   m->residual = take(T * c.hidden * 2);
   m->qkv = take(T * qkv_dim(c) * 2);
   m->attn = take(T * (int64_t)c.n_q_heads * c.head_dim * 2);
-  m->gate_up = take(T * 2 * (int64_t)c.intermediate * 2);
   m->act = take(T * (int64_t)c.intermediate * 2);
   m->sel = take(S * (int64_t)c.hidden * 2);
   m->logits = take(S * (int64_t)c.vocab * 2);

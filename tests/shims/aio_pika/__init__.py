@@ -262,7 +262,187 @@ class Connection(abc.AbstractConnection):
         await self.close()
 
 
-async def connect_robust(url: str = "amqp://guest:guest@localhost/", **kw) -> Connection:
+# ---- TCP mode: the same surface backed by tests/shims/aio_pika/server.py --------------------------
+class _RemoteIncoming(abc.AbstractIncomingMessage):
+    def __init__(self, chan: "RemoteChannel", m: dict):
+        self.body, self.message_id = m["body"], m.get("mid")
+        self.delivery_tag, self.redelivered = m["dtag"], m.get("red", False)
+        self.timestamp, self.headers = time.time(), {}
+        self._chan, self._done = chan, False
+
+    async def ack(self, multiple: bool = False) -> None:
+        if not self._done:
+            self._done = True
+            self._chan._send({"op": "ack", "cid": self._chan.cid, "dtag": self.delivery_tag})
+
+    async def reject(self, requeue: bool = False) -> None:
+        if not self._done:
+            self._done = True
+            self._chan._send({"op": "reject", "cid": self._chan.cid, "dtag": self.delivery_tag, "requeue": requeue})
+
+    async def nack(self, multiple: bool = False, requeue: bool = True) -> None:
+        await self.reject(requeue=requeue)
+
+
+class RemoteQueue(abc.AbstractQueue):
+    _ctags = itertools.count(1)
+
+    def __init__(self, chan: "RemoteChannel", name: str, count: int):
+        self.channel, self.name = chan, name
+        self.declaration_result = _PurgeOk(count)
+
+    async def consume(self, callback: Callable, no_ack: bool = False, **kw) -> str:
+        tag = f"ctag-{id(self.channel) & 0xffff}-{next(self._ctags)}"
+        self.channel._callbacks[tag] = (callback, no_ack)
+        await self.channel._call({"op": "consume", "name": self.name, "ctag": tag, "no_ack": no_ack})
+        return tag
+
+    async def cancel(self, consumer_tag: str, **kw) -> None:
+        await self.channel._call({"op": "cancel", "ctag": consumer_tag})
+        self.channel._callbacks.pop(consumer_tag, None)
+
+    async def purge(self, **kw) -> _PurgeOk:
+        r = await self.channel._call({"op": "purge", "name": self.name})
+        return _PurgeOk(r.get("count", 0))
+
+
+class _RemoteExchange:
+    def __init__(self, chan: "RemoteChannel"):
+        self._chan = chan
+
+    async def publish(self, message: Message, routing_key: str, **kw) -> None:
+        self._chan._send({"op": "publish", "key": routing_key, "body": message.body, "mid": message.message_id})
+        await self._chan._conn._drain()
+
+
+class RemoteChannel(abc.AbstractChannel):
+    def __init__(self, conn: "RemoteConnection", cid: int):
+        self._conn, self.cid = conn, cid
+        self._callbacks: Dict[str, tuple] = {}
+        self.closed = False
+        self.default_exchange = _RemoteExchange(self)
+
+    @property
+    def is_closed(self) -> bool:
+        return self.closed
+
+    def _send(self, m: dict) -> None:
+        m.setdefault("cid", self.cid)
+        self._conn._write(m)
+
+    async def _call(self, m: dict) -> dict:
+        m.setdefault("cid", self.cid)
+        return await self._conn._request(m)
+
+    async def set_qos(self, prefetch_count: int = 0, **kw) -> None:
+        await self._call({"op": "qos", "n": int(prefetch_count)})
+
+    async def declare_queue(self, name: Optional[str] = None, *, durable: bool = False,
+                            passive: bool = False, **kw) -> RemoteQueue:
+        r = await self._call({"op": "declare", "name": name, "passive": passive})
+        if not r.get("ok"):
+            raise ChannelNotFoundEntity(r.get("err", "NOT_FOUND"))
+        return RemoteQueue(self, name, r.get("count", 0))
+
+    async def close(self) -> None:
+        if not self.closed:
+            self.closed = True
+            try:
+                await self._call({"op": "close_channel"})
+            except Exception:
+                pass
+
+
+class RemoteConnection(abc.AbstractConnection):
+    def __init__(self, host: str, port: int):
+        self._host, self._port = host, port
+        self._reader = self._writer = None
+        self._pending: Dict[int, asyncio.Future] = {}
+        self._rids = itertools.count(1)
+        self._cids = itertools.count(1)
+        self._chans: Dict[int, RemoteChannel] = {}
+        self._tasks: set = set()
+        self.is_closed = False
+
+    async def _open(self):
+        from .server import read_frame  # noqa: F401
+
+        self._reader, self._writer = await asyncio.open_connection(self._host, self._port)
+        self._rx = asyncio.get_running_loop().create_task(self._read_loop())
+        return self
+
+    def _write(self, m: dict) -> None:
+        from .server import write_frame
+
+        write_frame(self._writer, m)
+
+    async def _drain(self):
+        await self._writer.drain()
+
+    async def _request(self, m: dict) -> dict:
+        rid = next(self._rids)
+        m["rid"] = rid
+        fut = asyncio.get_running_loop().create_future()
+        self._pending[rid] = fut
+        self._write(m)
+        await self._writer.drain()
+        return await fut
+
+    async def _read_loop(self):
+        from .server import read_frame
+
+        try:
+            while True:
+                m = await read_frame(self._reader)
+                if m["op"] == "reply":
+                    fut = self._pending.pop(m["rid"], None)
+                    if fut and not fut.done():
+                        fut.set_result(m)
+                elif m["op"] == "deliver":
+                    ch = self._chans.get(m["cid"])
+                    cb = ch._callbacks.get(m["ctag"]) if ch else None
+                    if cb:
+                        im = _RemoteIncoming(ch, m)
+                        if cb[1]:
+                            im._done = True
+                        t = asyncio.get_running_loop().create_task(_Broker._run(cb[0], im))
+                        self._tasks.add(t)
+                        t.add_done_callback(self._tasks.discard)
+        except (asyncio.IncompleteReadError, ConnectionError, asyncio.CancelledError):
+            pass
+        finally:
+            for fut in self._pending.values():
+                if not fut.done():
+                    fut.set_exception(ConnectionError("shim broker connection lost"))
+
+    async def channel(self, **kw) -> RemoteChannel:
+        cid = next(self._cids)
+        ch = self._chans[cid] = RemoteChannel(self, cid)
+        await ch._call({"op": "open"})
+        return ch
+
+    async def close(self) -> None:
+        if self.is_closed:
+            return
+        self.is_closed = True
+        for ch in self._chans.values():
+            await ch.close()
+        self._rx.cancel()
+        try:
+            self._writer.close()
+        except Exception:
+            pass
+
+
+async def connect_robust(url: str = "amqp://guest:guest@localhost/", **kw):
+    """in-process broker by default; B200Q_SHIM_BROKER=host:port selects the TCP broker server
+    (tests/shims/aio_pika/server.py) so that several processes share the queues"""
+    import os
+
+    target = os.environ.get("B200Q_SHIM_BROKER")
+    if target:
+        host, port = target.rsplit(":", 1)
+        return await RemoteConnection(host, int(port))._open()
     return Connection(url)
 
 

@@ -224,3 +224,16 @@ def test_pipeline_stage_routing_with_native_worker(patched):
     # from its last token w106: "w107 .. w112"; extras ride along
     assert got["p0"].result == "w107 w108 w109 w110 w111 w112"
     assert got["p0"].prompt == "w101 w102 w103 w104 w105 w106" and got["p0"].model_dump()["src"] == "s0"
+
+
+def test_cli_install_routes_the_vllm_slot_to_the_native_worker():
+    """`llmq worker run` lazily imports llmq.workers.vllm_worker.VLLMWorker (ref:llmq/cli/worker.py:20);
+    llmq_b200.cli.install() publishes that module with the native worker and adds `worker b200`"""
+    import importlib
+
+    from llmq_b200 import cli
+    cli.install()
+    mod = importlib.import_module("llmq.workers.vllm_worker")
+    assert mod.VLLMWorker is B200Worker
+    from llmq.cli import main as M
+    assert "b200" in M.worker.commands and "run" in M.worker.commands

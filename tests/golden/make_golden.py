@@ -49,6 +49,39 @@ def hf_model(d: LlamaDims, w, dtype):
     return m.to(dtype)
 
 
+GEMMA2_CASE = dict(hidden=256, n_layers=4, n_q_heads=4, n_kv_heads=2, head_dim=64, intermediate=512, vocab=512,
+                   query_pre_attn_scalar=64.0, sliding_window=16, max_pos=256)
+
+
+def gemma2_golden(out_dir):
+    """Gemma-2 (the next architecture): HF Gemma2ForCausalLM on CPU -> goldens for
+    oracle/gemma2.py; 48 tokens > the 16-token sliding window, so both layer types are exercised"""
+    from transformers import Gemma2Config, Gemma2ForCausalLM
+
+    from oracle.gemma2 import Gemma2Dims, random_gemma2_weights
+
+    d = Gemma2Dims(**GEMMA2_CASE)
+    w = random_gemma2_weights(d, seed=3)
+    cfg = Gemma2Config(hidden_size=d.hidden, num_hidden_layers=d.n_layers, num_attention_heads=d.n_q_heads,
+                       num_key_value_heads=d.n_kv_heads, head_dim=d.head_dim, intermediate_size=d.intermediate,
+                       vocab_size=d.vocab, sliding_window=d.sliding_window,
+                       query_pre_attn_scalar=int(d.query_pre_attn_scalar), max_position_embeddings=d.max_pos,
+                       attn_implementation="eager")
+    m = Gemma2ForCausalLM(cfg).eval()
+    sd = {k: v.float() for k, v in w.items()}
+    sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
+    m.load_state_dict(sd, strict=True)
+    ids = torch.tensor(np.random.default_rng(0).integers(0, d.vocab, size=48)[None])
+    with torch.no_grad():
+        l32 = m(ids).logits[0].numpy()
+        gen = m.generate(ids[:, :20], max_new_tokens=10, do_sample=False, pad_token_id=0)[0, 20:].numpy()
+        l16 = m.to(torch.bfloat16)(ids).logits[0].float().numpy()
+    np.savez_compressed(os.path.join(out_dir, "hf_gemma2_tiny.npz"), ids=ids[0].numpy(),
+                        logits_fp32=l32.astype(np.float32), logits_bf16=l16.astype(np.float16),
+                        greedy_prompt_len=20, greedy_fp32=gen)
+    return {"dims": GEMMA2_CASE, "weights_seed": 3}
+
+
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     meta = {}
@@ -69,6 +102,8 @@ def main():
                       "torch": torch.__version__}
     with open(os.path.join(out_dir, "hf_llama_meta.json"), "w") as f:
         json.dump(meta, f, indent=1)
+    with open(os.path.join(out_dir, "hf_gemma2_meta.json"), "w") as f:
+        json.dump(gemma2_golden(out_dir), f, indent=1)
     print("wrote", sorted(os.listdir(out_dir)))
 
 

@@ -73,3 +73,26 @@ def test_rope_llama3_scaling_matches_vllm_formula():
     ref = torch.where(wl < 8192 / 4.0, base, torch.where(wl > 8192 / 1.0, base / 32.0,
                                                        (1 - smooth) * base / 32.0 + smooth * base))
     assert torch.allclose(inv, ref, rtol=1e-6, atol=0)
+
+
+def test_gemma2_oracle_matches_hf_golden():
+    """SURVEY.md §8 f1 groundwork: the Gemma-2 restatement (soft-capping, sliding window, GeGLU,
+    (1+w) norms, post-norms, scaled tied embeddings) against transformers' Gemma2ForCausalLM"""
+    from oracle.gemma2 import Gemma2Dims, Gemma2Oracle, random_gemma2_weights
+    meta = json.load(open(os.path.join(G, "hf_gemma2_meta.json")))
+    d = Gemma2Dims(**meta["dims"])
+    w = random_gemma2_weights(d, seed=meta["weights_seed"])
+    z = np.load(os.path.join(G, "hf_gemma2_tiny.npz"))
+    ids = torch.tensor(z["ids"])
+    pos = torch.arange(len(ids))
+    lg32, _ = Gemma2Oracle(d, w, "fp32").forward(ids, pos)
+    assert np.abs(lg32.numpy() - z["logits_fp32"]).max() < 2e-5
+    lg16, _ = Gemma2Oracle(d, w, "bf16").forward(ids, pos)
+    ref16 = z["logits_bf16"].astype(np.float32)
+    assert np.abs(lg16.numpy() - ref16).max() <= 4 * 2.0 ** -7 * np.abs(ref16).max()
+    n0 = int(z["greedy_prompt_len"])
+    assert Gemma2Oracle(d, w, "fp32").greedy(z["ids"][:n0].tolist(), len(z["greedy_fp32"])) == z["greedy_fp32"].tolist()
+    # the sliding window really bites: widening it changes the logits of late positions
+    d_wide = Gemma2Dims(**{**meta["dims"], "sliding_window": 4096})
+    lgw, _ = Gemma2Oracle(d_wide, w, "fp32").forward(ids, pos)
+    assert (lgw[:16] - lg32[:16]).abs().max() < 1e-6 and (lgw[32:] - lg32[32:]).abs().max() > 1e-4

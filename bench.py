@@ -159,34 +159,52 @@ def cpu_reference_sample(model_key: str, prompt_tokens: int, out_tokens: int, bu
     import torch
 
     from llmq_b200.model import BUILTIN_SPECS
-    from oracle.model import LlamaDims, LlamaOracle
 
     spec = BUILTIN_SPECS[model_key]
     cores = usable_host_cores()
     torch.set_num_threads(cores)
-    dims = LlamaDims(hidden=spec.hidden, n_layers=spec.n_layers, n_q_heads=spec.n_q_heads,
-                     n_kv_heads=spec.n_kv_heads, head_dim=spec.head_dim, intermediate=spec.intermediate,
-                     vocab=spec.vocab, rms_eps=spec.rms_eps, rope_theta=spec.rope_theta,
-                     rope_scaling=spec.rope_scaling, tie_embeddings=spec.tie_embeddings, max_pos=512)
     g = torch.Generator().manual_seed(7)
     mat = lambda r, c: torch.randn(r, c, generator=g) * 0.02
-    qd, kd = dims.n_q_heads * dims.head_dim, dims.n_kv_heads * dims.head_dim
-    layer = {"input_layernorm.weight": torch.ones(dims.hidden), "post_attention_layernorm.weight": torch.ones(dims.hidden),
-             "self_attn.q_proj.weight": mat(qd, dims.hidden), "self_attn.k_proj.weight": mat(kd, dims.hidden),
-             "self_attn.v_proj.weight": mat(kd, dims.hidden), "self_attn.o_proj.weight": mat(dims.hidden, qd),
-             "mlp.gate_proj.weight": mat(dims.intermediate, dims.hidden), "mlp.up_proj.weight": mat(dims.intermediate, dims.hidden),
-             "mlp.down_proj.weight": mat(dims.hidden, dims.intermediate)}
-    w = {"model.embed_tokens.weight": mat(dims.vocab, dims.hidden), "model.norm.weight": torch.ones(dims.hidden)}
-    if not dims.tie_embeddings:
+    qd, kd = spec.n_q_heads * spec.head_dim, spec.n_kv_heads * spec.head_dim
+    gemma = spec.arch == "gemma2"
+    norm = lambda: torch.zeros(spec.hidden) if gemma else torch.ones(spec.hidden)  # (1+w) vs w
+    norm_names = (["input_layernorm", "post_attention_layernorm", "pre_feedforward_layernorm",
+                   "post_feedforward_layernorm"] if gemma else ["input_layernorm", "post_attention_layernorm"])
+    layer = {f"{n}.weight": norm() for n in norm_names}
+    layer.update({"self_attn.q_proj.weight": mat(qd, spec.hidden), "self_attn.k_proj.weight": mat(kd, spec.hidden),
+                  "self_attn.v_proj.weight": mat(kd, spec.hidden), "self_attn.o_proj.weight": mat(spec.hidden, qd),
+                  "mlp.gate_proj.weight": mat(spec.intermediate, spec.hidden),
+                  "mlp.up_proj.weight": mat(spec.intermediate, spec.hidden),
+                  "mlp.down_proj.weight": mat(spec.hidden, spec.intermediate)})
+    w = {"model.embed_tokens.weight": mat(spec.vocab, spec.hidden), "model.norm.weight": norm()}
+    if not spec.tie_embeddings:
         w["lm_head.weight"] = w["model.embed_tokens.weight"]  # same shape; shares storage
-    for i in range(dims.n_layers):
+    for i in range(spec.n_layers):
         for k, v in layer.items():
             w[f"model.layers.{i}.{k}"] = v
-    oracle = LlamaOracle.__new__(LlamaOracle)  # skip the per-tensor copies of __init__
     from oracle import ops as O
-    oracle.d, oracle.mode, oracle.w = dims, "fp32", w
-    oracle.table = O.rope_table(512, dims.head_dim, dims.rope_theta, dims.rope_scaling, "fp32")
-    oracle.scale = dims.head_dim ** -0.5
+    if gemma:
+        from oracle.gemma2 import Gemma2Dims, Gemma2Oracle
+        dims = Gemma2Dims(hidden=spec.hidden, n_layers=spec.n_layers, n_q_heads=spec.n_q_heads,
+                          n_kv_heads=spec.n_kv_heads, head_dim=spec.head_dim, intermediate=spec.intermediate,
+                          vocab=spec.vocab, rms_eps=spec.rms_eps, rope_theta=spec.rope_theta,
+                          query_pre_attn_scalar=spec.query_pre_attn_scalar or spec.head_dim,
+                          attn_softcap=spec.attn_softcap or None, final_softcap=spec.final_softcap or None,
+                          sliding_window=spec.sliding_window or 4096, max_pos=512)
+        oracle = Gemma2Oracle.__new__(Gemma2Oracle)  # skip the per-tensor copies of __init__
+        oracle.d, oracle.mode, oracle.w = dims, "fp32", w
+        oracle.table = O.rope_table(512, dims.head_dim, dims.rope_theta, None, "fp32")
+        oracle.scale = dims.query_pre_attn_scalar ** -0.5
+    else:
+        from oracle.model import LlamaDims, LlamaOracle
+        dims = LlamaDims(hidden=spec.hidden, n_layers=spec.n_layers, n_q_heads=spec.n_q_heads,
+                         n_kv_heads=spec.n_kv_heads, head_dim=spec.head_dim, intermediate=spec.intermediate,
+                         vocab=spec.vocab, rms_eps=spec.rms_eps, rope_theta=spec.rope_theta,
+                         rope_scaling=spec.rope_scaling, tie_embeddings=spec.tie_embeddings, max_pos=512)
+        oracle = LlamaOracle.__new__(LlamaOracle)  # skip the per-tensor copies of __init__
+        oracle.d, oracle.mode, oracle.w = dims, "fp32", w
+        oracle.table = O.rope_table(512, dims.head_dim, dims.rope_theta, dims.rope_scaling, "fp32")
+        oracle.scale = dims.head_dim ** -0.5
     ids = torch.randint(0, dims.vocab, (prompt_tokens,), generator=g)
 
     def sample():
@@ -223,7 +241,7 @@ def run_reference(args):
     tps = statistics.median(r["tokens_per_s"] for r in res)
     desc = (f"1 job per step on {cores} host threads (torch-CPU fp32 oracle, one batch row): real {args.prompt_tokens}-token prefill + "
             f"{res[0]['decode_steps_timed']} timed greedy decode steps, extrapolated to {args.out_tokens} output tokens; "
-            "32 layers share one random layer's weights")
+            "all decoder layers share one random layer's weights")
     line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cpu)", "data": "synthetic",
@@ -430,7 +448,7 @@ def run_native(args):
                    "jobs_per_sec": r["jobs_per_s"],
                    "sample": f"1 job: real {args.prompt_tokens}-token prefill ({r['t_prefill_s']:.2f} s) + {r['decode_steps_timed']} timed decode "
                              f"steps ({r['s_per_decode_token'] * 1e3:.1f} ms/token) extrapolated to {args.out_tokens} out tokens; torch-CPU fp32 "
-                             "oracle, all host threads, 32 layers share one random layer's weights"}
+                             "oracle, all host threads, all decoder layers share one random layer's weights"}
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(total_a / args.steps * 1e3, 2), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",

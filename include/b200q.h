@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200Q_VERSION 1
+#define B200Q_VERSION 2
 
 #define B200Q_OK 0
 #define B200Q_EINVAL (-1)   /* bad argument / unsupported shape            */
@@ -122,6 +122,46 @@ int b200q_argmax_bf16(const void* logits_dev, int32_t* ids_dev, int B, int V, vo
 int b200q_sample_bf16(const void* logits_dev, const int32_t* params_dev, int32_t* ids_dev,
                       int B, int V, void* stream);
 
+/* ---- Gemma-2 family (vllm/model_executor/models/gemma2.py) ----------------- */
+
+/* embedding gather with the Gemma normaliser: out[t,:] = bf16(table[ids[t],:] * scale), scale =
+ *     bf16(sqrt(H))                                                    (gemma2.py embed_tokens * normalizer) */
+int b200q_embed_scaled(const int32_t* ids_dev, const void* table_dev, void* out_dev,
+                       int T, int H, float scale, void* stream);
+
+/* GemmaRMSNorm: y = bf16(x * rsqrt(mean(x^2)+eps) * (1 + w)), ONE rounding
+ *     (vllm/model_executor/layers/layernorm.py GemmaRMSNorm.forward_static) */
+int b200q_gemma_rmsnorm(const void* x_dev, const void* w_dev, void* y_dev,
+                        int T, int H, float eps, void* stream);
+
+/* Gemma-2 sandwich norms around the residual add, fused, in place:
+ *     residual <- bf16(residual + gemma_rmsnorm(x, w_post));  x <- gemma_rmsnorm(residual, w_next)
+ *     (post_attention_layernorm + pre_feedforward_layernorm, or post_feedforward_layernorm + the
+ *     next layer's input_layernorm / the final norm; gemma2.py Gemma2DecoderLayer.forward) */
+int b200q_gemma_norm_add_norm(void* x_dev, void* residual_dev, const void* w_post_dev,
+                              const void* w_next_dev, int T, int H, float eps, void* stream);
+
+/* K7/K6 with Gemma-2's attention extras: scores <- softcap * tanh(scores * scale / softcap)
+ *     (softcap <= 0: off) and a sliding window: the query at position p sees keys j with
+ *     p - window < j <= p (window <= 0: off).  D in {64, 128, 256}. */
+int b200q_decode_attn_ex(const void* q_dev, int q_stride, void* out_dev, const void* kv_layer_dev,
+                         const int32_t* block_table_dev, int bt_stride, const int32_t* ctx_lens_dev,
+                         int n_seqs, int n_q, int n_kv, int D, int block_size, float scale,
+                         float softcap, int window, void* stream);
+int b200q_prefill_attn_ex(const void* q_dev, int q_stride, void* out_dev, const void* kv_layer_dev,
+                          const int32_t* block_table_dev, int bt_stride, const int32_t* tiles_dev,
+                          int n_tiles, int n_q, int n_kv, int D, int block_size, float scale,
+                          float softcap, int window, void* stream);
+
+/* fused gate_up GEMM + GeGLU: out = bf16(bf16(gelu_tanh(g)) * u), weight rows interleaved exactly as
+ *     for b200q_gemm_swiglu_bf16                          (vllm activation.py GeluAndMul, approximate="tanh") */
+int b200q_gemm_geglu_bf16(const void* A_dev, const void* W_dev, void* C_dev,
+                          int M, int N, int K, void* stream);
+
+/* final-logit soft-capping in place over n bf16 values, with the bf16 rounding of every eager op:
+ *     l <- bf16(bf16(tanh(bf16(l / cap))) * cap)               (vllm logits_processor.py:66-69) */
+int b200q_softcap_bf16(void* logits_dev, int64_t n, float cap, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Model-level: one forward step over a mixed decode+prefill token batch.
  * Replaces GPUModelRunner.execute_model for LlamaForCausalLM
@@ -133,7 +173,7 @@ typedef struct b200q_model_config {
   int32_t n_layers;      /* L                              */
   int32_t n_q_heads;
   int32_t n_kv_heads;
-  int32_t head_dim;      /* 64 or 128                      */
+  int32_t head_dim;      /* 64, 128 or 256                 */
   int32_t intermediate;  /* I                              */
   int32_t vocab;         /* V                              */
   int32_t block_size;    /* KV page size in tokens (16)    */
@@ -142,8 +182,17 @@ typedef struct b200q_model_config {
   int32_t max_pos;       /* rows of the RoPE table         */
   int32_t tie_embeddings;/* 1: lm_head shares embed_tokens */
   float rms_eps;
-  float attn_scale;      /* 1/sqrt(head_dim)               */
+  float attn_scale;      /* 1/sqrt(head_dim); gemma2: query_pre_attn_scalar^-0.5 */
+  /* architecture extras; all zero = Llama */
+  int32_t arch;           /* B200Q_ARCH_LLAMA | B200Q_ARCH_GEMMA2                                   */
+  int32_t sliding_window; /* gemma2: even layers see only the last `sliding_window` keys; 0 = off   */
+  float attn_softcap;     /* attention logit soft-capping (gemma2: 50); 0 = off                     */
+  float final_softcap;    /* final logit soft-capping (gemma2: 30); 0 = off                         */
+  float embed_scale;      /* embeddings are multiplied by this value (gemma2: bf16(sqrt(H))); 0 = off */
 } b200q_model_config;
+
+#define B200Q_ARCH_LLAMA 0
+#define B200Q_ARCH_GEMMA2 1
 
 typedef struct b200q_model* b200q_model_t;
 
@@ -174,7 +223,9 @@ int b200q_model_destroy(b200q_model_t m);
 /* names: "embed", "final_norm", "lm_head", and per layer i: "layers.i.input_norm",
  * "layers.i.qkv" [(n_q+2n_kv)D, H], "layers.i.o" [H, n_q D], "layers.i.post_norm",
  * "layers.i.gate_up" [2I, H] (gate/up rows interleaved in 128-row blocks, see
- * b200q_gemm_swiglu_bf16), "layers.i.down" [H, I].  bf16, row-major, contiguous. */
+ * b200q_gemm_swiglu_bf16), "layers.i.down" [H, I].  bf16, row-major, contiguous.
+ * B200Q_ARCH_GEMMA2 replaces "post_norm" by the three norms "layers.i.post_attn_norm",
+ * "layers.i.pre_ffn_norm", "layers.i.post_ffn_norm" (weights as stored: the kernels add the 1). */
 int b200q_model_bind_weight(b200q_model_t m, const char* name, const void* dev_ptr,
                             int64_t rows, int64_t cols);
 /* kv: [L][num_blocks][2][n_kv][block_size][D] bf16, zero-initialised by the caller */

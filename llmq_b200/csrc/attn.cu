@@ -18,13 +18,28 @@
 //   warps (one per query head of the group) share a 4-stage page ring filled by a producer
 //   warp; causal masking by absolute position; K/V are read back from the paged cache, so
 //   chunked prefill over an existing context needs no special case.
+// Gemma-2 extras, compiled as separate instantiations so the Llama kernels keep
+// their code: kCap = attention-logit soft-capping (score <- cap * tanh(score * scale / cap)), and a
+// runtime sliding window (query at position p sees keys p - window < j <= p; pages that lie entirely
+// before the window are never fetched).  D = 256 (Gemma-2 head size) uses 2-stage rings.
 #include "common.cuh"
 
 namespace b200q {
 
 constexpr int DEC_WARPS = 4;
-constexpr int DEC_STAGES = 3;
 constexpr int PF_STAGES = 4;
+// decode ring depth per warp: 3 pages of K+V in flight (2 at D = 256, where a page is 8 KB)
+template <int D>
+struct DecCfg {
+  static constexpr int STAGES = D > 128 ? 2 : 3;
+};
+
+// score -> log2-domain logit.  plain: s * (scale * log2 e).  capped: tanh(s * scale / cap) * (cap * log2 e)
+template <bool kCap>
+__device__ __forceinline__ float score_xform(float s, float c0, float c1) {
+  if (kCap) return tanhf(s * c0) * c1;
+  return s * c0;
+}
 
 template <int D, int BS>
 struct Geo {
@@ -105,21 +120,23 @@ __device__ __forceinline__ void zero_tail_rows(uint8_t* v_page, int n_valid, int
 // ------------------------------------------------------------------------------------------
 template <int D, int BS>
 struct DecSmem {
+  static constexpr int STAGES = DecCfg<D>::STAGES;
   static constexpr int STAGE_BYTES = 2 * Geo<D, BS>::PAGE_BYTES;
-  static constexpr int RING_BYTES = DEC_WARPS * DEC_STAGES * STAGE_BYTES;
+  static constexpr int RING_BYTES = DEC_WARPS * STAGES * STAGE_BYTES;
   static constexpr int MERGE_FLOATS = DEC_WARPS * 8 * (D + 2);
-  static constexpr int TOTAL = RING_BYTES + MERGE_FLOATS * 4 + DEC_WARPS * DEC_STAGES * 8;
+  static constexpr int TOTAL = RING_BYTES + MERGE_FLOATS * 4 + DEC_WARPS * STAGES * 8;
 };
 
-template <int D, int BS>
+template <int D, int BS, bool kCap>
 __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
     decode_attn_kernel(const bf16* __restrict__ q, int q_stride, bf16* __restrict__ out,
                        const uint8_t* __restrict__ kv_layer,
                        const int32_t* __restrict__ block_table, int bt_stride,
                        const int32_t* __restrict__ ctx_lens, int n_q, int n_kv, int G,
-                       float scale_log2) {
+                       float c0, float c1, int window) {
   using G_ = Geo<D, BS>;
   using S_ = DecSmem<D, BS>;
+  constexpr int DEC_STAGES = S_::STAGES;
   extern __shared__ __align__(128) uint8_t smem[];
   const int seq = blockIdx.x, kvh = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -129,7 +146,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
                    warp * DEC_STAGES;
 
   const int ctx = __ldg(ctx_lens + seq);
-  const int n_pages = (ctx + BS - 1) / BS;
+  // the query sits at position ctx-1 and sees keys [lo, ctx); pages before lo's page are skipped
+  const int lo = (window > 0 && ctx > window) ? ctx - window : 0;
+  const int page0 = lo / BS;
+  const int n_pages = (ctx + BS - 1) / BS - page0;
   const int my_n = n_pages > warp ? (n_pages - warp + DEC_WARPS - 1) / DEC_WARPS : 0;
 
   if (lane == 0) {
@@ -139,7 +159,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
   }
   __syncwarp();
 
-  const int32_t* bt = block_table + (long long)seq * bt_stride;
+  const int32_t* bt = block_table + (long long)seq * bt_stride + page0;
   const long long page_stride = (long long)G_::PAGE_BYTES;  // bytes per (block,kv,head) page
   // page address: ((blk*2 + kv) * n_kv + kvh) * PAGE_BYTES
   int ids_base = 0;
@@ -151,7 +171,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
       ids = (ids_base + lane < my_n) ? __ldg(bt + warp + DEC_WARPS * (ids_base + lane)) : 0;
     }
     const int blk = __shfl_sync(0xffffffffu, ids, k - ids_base);
-    const int p = warp + DEC_WARPS * k;
+    const int p = page0 + warp + DEC_WARPS * k;
     const int n_valid = min(BS, ctx - p * BS);
     const int st = k % DEC_STAGES;
     uint8_t* ks = ring + st * S_::STAGE_BYTES;
@@ -196,8 +216,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
     const int st = k % DEC_STAGES;
     const uint32_t phase = (uint32_t)(k / DEC_STAGES) & 1u;
     mbar_wait(bars + st, phase);
-    const int p = warp + DEC_WARPS * k;
+    const int p = page0 + warp + DEC_WARPS * k;
     const int n_valid = min(BS, ctx - p * BS);
+    const int t_lo = lo - p * BS;  // first visible token of this page (<= 0 except on the window's first page)
     const uint32_t k_s = smem_u32(ring + st * S_::STAGE_BYTES);
     const uint32_t v_s = k_s + G_::PAGE_BYTES;
 
@@ -208,8 +229,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
 #pragma unroll
     for (int nt = 0; nt < G_::NT; ++nt) {
       const int t0 = nt * 8 + (lane & 3) * 2;
-      s[nt][0] = (t0 < n_valid) ? s[nt][0] * scale_log2 : -INFINITY;
-      s[nt][1] = (t0 + 1 < n_valid) ? s[nt][1] * scale_log2 : -INFINITY;
+      s[nt][0] = (t0 < n_valid && t0 >= t_lo) ? score_xform<kCap>(s[nt][0], c0, c1) : -INFINITY;
+      s[nt][1] = (t0 + 1 < n_valid && t0 + 1 >= t_lo) ? score_xform<kCap>(s[nt][1], c0, c1) : -INFINITY;
       mx = fmaxf(mx, fmaxf(s[nt][0], s[nt][1]));
     }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -287,20 +308,22 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
 // ------------------------------------------------------------------------------------------
 template <int D, int BS>
 struct Dec2Smem {
+  static constexpr int STAGES = DecCfg<D>::STAGES;
   static constexpr int STAGE_BYTES = 2 * Geo<D, BS>::PAGE_BYTES;
-  static constexpr int RING_BYTES = DEC_WARPS * DEC_STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = RING_BYTES + DEC_WARPS * DEC_STAGES * 8;
+  static constexpr int RING_BYTES = DEC_WARPS * STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = RING_BYTES + DEC_WARPS * STAGES * 8;
 };
 
-template <int D, int BS>
+template <int D, int BS, bool kCap>
 __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
     decode_attn_stream_kernel(const bf16* __restrict__ q, int q_stride, bf16* __restrict__ out,
                               const uint8_t* __restrict__ kv_layer,
                               const int32_t* __restrict__ block_table, int bt_stride,
                               const int32_t* __restrict__ ctx_lens, int n_seqs, int n_q, int n_kv,
-                              int G, float scale_log2) {
+                              int G, float c0, float c1, int window) {
   using G_ = Geo<D, BS>;
   using S_ = Dec2Smem<D, BS>;
+  constexpr int DEC_STAGES = S_::STAGES;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* ring = smem + warp * DEC_STAGES * S_::STAGE_BYTES;
@@ -321,10 +344,15 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
   const int r = lane >> 2, cq = (lane & 3) * 2;
 
   // ---- issue cursor: runs up to DEC_STAGES pages ahead of the consumer, across item borders ----
-  int i_item = first, i_page = 0, i_ctx = max(__ldg(ctx_lens + first / n_kv), 1);
+  // with a sliding window an item's pages run from first_page(ctx) to the last one
+  auto first_page = [&](int ctx) { return (window > 0 && ctx > window) ? (ctx - window) / BS : 0; };
+  int i_item = first, i_ctx = max(__ldg(ctx_lens + first / n_kv), 1);
+  int i_page = first_page(i_ctx);
   int i_npages = (i_ctx + BS - 1) / BS;
-  int i_ids_base = 0;
-  int i_ids = (lane < i_npages) ? __ldg(block_table + (long long)(first / n_kv) * bt_stride + lane) : 0;
+  int i_ids_base = i_page;
+  int i_ids = (i_ids_base + lane < i_npages)
+                  ? __ldg(block_table + (long long)(first / n_kv) * bt_stride + i_ids_base + lane)
+                  : 0;
   int issued = 0;
   bool i_done = false;
   auto issue_next = [&]() {  // whole warp
@@ -363,9 +391,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
       const int seq = i_item / n_kv;
       i_ctx = max(__ldg(ctx_lens + seq), 1);
       i_npages = (i_ctx + BS - 1) / BS;
-      i_page = 0;
-      i_ids_base = 0;
-      i_ids = (lane < i_npages) ? __ldg(block_table + (long long)seq * bt_stride + lane) : 0;
+      i_page = first_page(i_ctx);
+      i_ids_base = i_page;
+      i_ids = (i_ids_base + lane < i_npages)
+                  ? __ldg(block_table + (long long)seq * bt_stride + i_ids_base + lane)
+                  : 0;
     }
   };
   for (int k = 0; k < DEC_STAGES; ++k) issue_next();
@@ -395,6 +425,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
     }
     const int ctx = n_ctx;
     const int n_pages = (ctx + BS - 1) / BS;
+    const int lo = (window > 0 && ctx > window) ? ctx - window : 0;
     if (item + n_warps < total) {  // prefetch the next item's Q and context length
       n_ctx = max(__ldg(ctx_lens + (item + n_warps) / n_kv), 1);
       load_q(item + n_warps, qn);
@@ -403,10 +434,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m = -INFINITY, l = 0.f;
-    for (int p = 0; p < n_pages; ++p) {
+    for (int p = lo / BS; p < n_pages; ++p) {
       const int st = consumed % DEC_STAGES;
       mbar_wait(bars + st, (uint32_t)(consumed / DEC_STAGES) & 1u);
       const int n_valid = min(BS, ctx - p * BS);
+      const int t_lo = lo - p * BS;
       const uint32_t k_s = smem_u32(ring + st * S_::STAGE_BYTES);
       const uint32_t v_s = k_s + G_::PAGE_BYTES;
       float s[BS / 8][4];
@@ -415,8 +447,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
 #pragma unroll
       for (int nt = 0; nt < G_::NT; ++nt) {
         const int t0 = nt * 8 + cq;
-        s[nt][0] = (t0 < n_valid) ? s[nt][0] * scale_log2 : -INFINITY;
-        s[nt][1] = (t0 + 1 < n_valid) ? s[nt][1] * scale_log2 : -INFINITY;
+        s[nt][0] = (t0 < n_valid && t0 >= t_lo) ? score_xform<kCap>(s[nt][0], c0, c1) : -INFINITY;
+        s[nt][1] = (t0 + 1 < n_valid && t0 + 1 >= t_lo) ? score_xform<kCap>(s[nt][1], c0, c1) : -INFINITY;
         mx = fmaxf(mx, fmaxf(s[nt][0], s[nt][1]));
       }
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -467,13 +499,19 @@ struct PfSmem {
   static constexpr int TOTAL = RING_BYTES + 2 * PF_STAGES * 8;
 };
 
-template <int D, int BS>
-__global__ void __launch_bounds__(9 * 32)
+// consumer warps + 1 producer: G <= 8 (G <= 4 at D = 256, whose O accumulators need the registers)
+template <int D>
+struct PfCfg {
+  static constexpr int MAX_G = D > 128 ? 4 : 8;
+};
+
+template <int D, int BS, bool kCap>
+__global__ void __launch_bounds__((PfCfg<D>::MAX_G + 1) * 32)
     prefill_attn_kernel(const bf16* __restrict__ q, int q_stride, bf16* __restrict__ out,
                         const uint8_t* __restrict__ kv_layer,
                         const int32_t* __restrict__ block_table, int bt_stride,
                         const int4* __restrict__ tiles, int n_q, int n_kv, int G,
-                        float scale_log2) {
+                        float c0, float c1, int window) {
   using G_ = Geo<D, BS>;
   using S_ = PfSmem<D, BS>;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -485,6 +523,9 @@ __global__ void __launch_bounds__(9 * 32)
   const int bt_row = tile.x, row0 = tile.y, n_rows = tile.z, pos0 = tile.w;
   const int total_kv = pos0 + n_rows;  // keys 0 .. pos0+n_rows-1 are visible to this tile
   const int n_pages = (total_kv + BS - 1) / BS;
+  // sliding window: row i (position pos0+i) sees keys j > pos0+i-window; the tile starts at the
+  // page holding row 0's first visible key
+  const int page0 = (window > 0 && pos0 + 1 > window) ? (pos0 + 1 - window) / BS : 0;
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -499,9 +540,10 @@ __global__ void __launch_bounds__(9 * 32)
   if (warp == G) {
     // ===== producer warp: TMA page gather through the block table =====
     const int32_t* bt = block_table + (long long)bt_row * bt_stride;
-    for (int p = 0; p < n_pages; ++p) {
-      const int st = p % PF_STAGES;
-      if (p >= PF_STAGES) mbar_wait(empty + st, (uint32_t)((p / PF_STAGES) - 1) & 1u);
+    for (int p = page0; p < n_pages; ++p) {
+      const int it = p - page0;
+      const int st = it % PF_STAGES;
+      if (it >= PF_STAGES) mbar_wait(empty + st, (uint32_t)((it / PF_STAGES) - 1) & 1u);
       const int n_valid = min(BS, total_kv - p * BS);
       uint8_t* ks = smem + st * S_::STAGE_BYTES;
       uint8_t* vs = ks + G_::PAGE_BYTES;
@@ -546,12 +588,15 @@ __global__ void __launch_bounds__(9 * 32)
 #pragma unroll
   for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  // last visible key index per row (causal), clamped to the keys that exist
+  // last visible key index per row (causal), clamped to the keys that exist; first visible key
+  // under the sliding window
   const int lim0 = min(pos0 + r, total_kv - 1), lim1 = min(pos0 + r + 8, total_kv - 1);
+  const int lo0 = window > 0 ? pos0 + r + 1 - window : 0, lo1 = window > 0 ? lo0 + 8 : 0;
 
-  for (int p = 0; p < n_pages; ++p) {
-    const int st = p % PF_STAGES;
-    mbar_wait(full + st, (uint32_t)(p / PF_STAGES) & 1u);
+  for (int p = page0; p < n_pages; ++p) {
+    const int it = p - page0;
+    const int st = it % PF_STAGES;
+    mbar_wait(full + st, (uint32_t)(it / PF_STAGES) & 1u);
     const uint32_t k_s = smem_u32(smem + st * S_::STAGE_BYTES);
     const uint32_t v_s = k_s + G_::PAGE_BYTES;
     float s[BS / 8][4];
@@ -560,10 +605,10 @@ __global__ void __launch_bounds__(9 * 32)
 #pragma unroll
     for (int nt = 0; nt < G_::NT; ++nt) {
       const int j = p * BS + nt * 8 + cq;
-      s[nt][0] = (j <= lim0) ? s[nt][0] * scale_log2 : -INFINITY;
-      s[nt][1] = (j + 1 <= lim0) ? s[nt][1] * scale_log2 : -INFINITY;
-      s[nt][2] = (j <= lim1) ? s[nt][2] * scale_log2 : -INFINITY;
-      s[nt][3] = (j + 1 <= lim1) ? s[nt][3] * scale_log2 : -INFINITY;
+      s[nt][0] = (j <= lim0 && j >= lo0) ? score_xform<kCap>(s[nt][0], c0, c1) : -INFINITY;
+      s[nt][1] = (j + 1 <= lim0 && j + 1 >= lo0) ? score_xform<kCap>(s[nt][1], c0, c1) : -INFINITY;
+      s[nt][2] = (j <= lim1 && j >= lo1) ? score_xform<kCap>(s[nt][2], c0, c1) : -INFINITY;
+      s[nt][3] = (j + 1 <= lim1 && j + 1 >= lo1) ? score_xform<kCap>(s[nt][3], c0, c1) : -INFINITY;
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -571,16 +616,19 @@ __global__ void __launch_bounds__(9 * 32)
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    // key 0 is visible to every row, so after page 0 both maxima are finite
+    // without a window key 0 is visible to every row and the maxima are finite after page 0; with
+    // one, a row may not have met a visible key yet (m = -inf): subtract 0 instead of -inf then, so
+    // that alpha and the probabilities come out as exact zeros, not NaN
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    const float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+    const float b0 = mn0 == -INFINITY ? 0.f : mn0, b1 = mn1 == -INFINITY ? 0.f : mn1;
+    const float a0 = exp2f(m0 - b0), a1 = exp2f(m1 - b1);
     float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < G_::NT; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - mn0);
-      s[nt][1] = exp2f(s[nt][1] - mn0);
-      s[nt][2] = exp2f(s[nt][2] - mn1);
-      s[nt][3] = exp2f(s[nt][3] - mn1);
+      s[nt][0] = exp2f(s[nt][0] - b0);
+      s[nt][1] = exp2f(s[nt][1] - b0);
+      s[nt][2] = exp2f(s[nt][2] - b1);
+      s[nt][3] = exp2f(s[nt][3] - b1);
       ps0 += s[nt][0] + s[nt][1];
       ps1 += s[nt][2] + s[nt][3];
     }
@@ -615,21 +663,32 @@ __global__ void __launch_bounds__(9 * 32)
   }
 }
 
-template <int D, int BS>
+// c0/c1 of score_xform for a given scale / soft cap
+struct ScoreConsts {
+  float c0, c1;
+};
+static inline ScoreConsts score_consts(float scale, float softcap) {
+  const float log2e = 1.4426950408889634f;
+  if (softcap > 0.f) return {scale / softcap, softcap * log2e};
+  return {scale * log2e, 0.f};
+}
+
+template <int D, int BS, bool kCap>
 static int launch_decode(const void* q, int q_stride, void* out, const void* kv,
                          const int32_t* bt, int bt_stride, const int32_t* ctx, int n_seqs, int n_q,
-                         int n_kv, float scale, cudaStream_t st) {
+                         int n_kv, float scale, float softcap, int window, cudaStream_t st) {
   using S_ = DecSmem<D, BS>;
-  auto kern = decode_attn_kernel<D, BS>;
+  auto kern = decode_attn_kernel<D, BS, kCap>;
   static bool attr_set = false;
   if (!attr_set) {
     B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::TOTAL));
     attr_set = true;
   }
+  const ScoreConsts sc = score_consts(scale, softcap);
   dim3 grid(n_seqs, n_kv);
   kern<<<grid, DEC_WARPS * 32, S_::TOTAL, st>>>((const bf16*)q, q_stride, (bf16*)out,
                                                 (const uint8_t*)kv, bt, bt_stride, ctx, n_q, n_kv,
-                                                n_q / n_kv, scale * 1.4426950408889634f);
+                                                n_q / n_kv, sc.c0, sc.c1, window);
   B200Q_LAUNCH_CHECK();
   return B200Q_OK;
 }
@@ -647,12 +706,13 @@ static int attn_num_sms() {
   return n;
 }
 
-template <int D, int BS>
+template <int D, int BS, bool kCap>
 static int launch_decode_stream(const void* q, int q_stride, void* out, const void* kv,
                                 const int32_t* bt, int bt_stride, const int32_t* ctx, int n_seqs,
-                                int n_q, int n_kv, float scale, cudaStream_t st) {
+                                int n_q, int n_kv, float scale, float softcap, int window,
+                                cudaStream_t st) {
   using S_ = Dec2Smem<D, BS>;
-  auto kern = decode_attn_stream_kernel<D, BS>;
+  auto kern = decode_attn_stream_kernel<D, BS, kCap>;
   static bool attr_set = false;
   if (!attr_set) {
     B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::TOTAL));
@@ -664,33 +724,47 @@ static int launch_decode_stream(const void* q, int q_stride, void* out, const vo
   const int max_ctas = g_decode_variant == 3 ? 4 : 2 * attn_num_sms();
   const int want = (total + DEC_WARPS - 1) / DEC_WARPS;
   const int grid = want < max_ctas ? want : max_ctas;
+  const ScoreConsts sc = score_consts(scale, softcap);
   kern<<<grid, DEC_WARPS * 32, S_::TOTAL, st>>>((const bf16*)q, q_stride, (bf16*)out,
                                                 (const uint8_t*)kv, bt, bt_stride, ctx, n_seqs, n_q,
-                                                n_kv, n_q / n_kv, scale * 1.4426950408889634f);
+                                                n_kv, n_q / n_kv, sc.c0, sc.c1, window);
   B200Q_LAUNCH_CHECK();
   return B200Q_OK;
 }
 
-template <int D, int BS>
+template <int D, int BS, bool kCap>
 static int launch_prefill(const void* q, int q_stride, void* out, const void* kv,
                           const int32_t* bt, int bt_stride, const int32_t* tiles, int n_tiles,
-                          int n_q, int n_kv, float scale, cudaStream_t st) {
+                          int n_q, int n_kv, float scale, float softcap, int window,
+                          cudaStream_t st) {
   using S_ = PfSmem<D, BS>;
-  auto kern = prefill_attn_kernel<D, BS>;
+  auto kern = prefill_attn_kernel<D, BS, kCap>;
   static bool attr_set = false;
   if (!attr_set) {
     B200Q_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::TOTAL));
     attr_set = true;
   }
   const int G = n_q / n_kv;
+  B200Q_CHECK_ARG(G <= PfCfg<D>::MAX_G, "prefill_attn: GQA group %d too large for D=%d (max %d)", G, D,
+                  PfCfg<D>::MAX_G);
+  const ScoreConsts sc = score_consts(scale, softcap);
   dim3 grid(n_tiles, n_kv);
   kern<<<grid, (G + 1) * 32, S_::TOTAL, st>>>((const bf16*)q, q_stride, (bf16*)out,
                                               (const uint8_t*)kv, bt, bt_stride,
-                                              (const int4*)tiles, n_q, n_kv, G,
-                                              scale * 1.4426950408889634f);
+                                              (const int4*)tiles, n_q, n_kv, G, sc.c0, sc.c1, window);
   B200Q_LAUNCH_CHECK();
   return B200Q_OK;
 }
+
+// (D, soft-cap) dispatch: the capped variants exist for every D so that small test models can use
+// them; the uncapped D = 64 / 128 instantiations are the Llama kernels.
+#define B200Q_ATTN_DISPATCH(FN, ...)                                     \
+  do {                                                                   \
+    const bool cap = softcap > 0.f;                                      \
+    if (D == 64) return cap ? FN<64, 16, true>(__VA_ARGS__) : FN<64, 16, false>(__VA_ARGS__);    \
+    if (D == 128) return cap ? FN<128, 16, true>(__VA_ARGS__) : FN<128, 16, false>(__VA_ARGS__); \
+    return cap ? FN<256, 16, true>(__VA_ARGS__) : FN<256, 16, false>(__VA_ARGS__);               \
+  } while (0)
 
 }  // namespace b200q
 
@@ -706,15 +780,15 @@ int b200q_decode_attn_set_variant(int v) {
   return B200Q_OK;
 }
 
-int b200q_decode_attn(const void* q, int q_stride, void* out, const void* kv_layer,
-                      const int32_t* block_table, int bt_stride, const int32_t* ctx_lens,
-                      int n_seqs, int n_q, int n_kv, int D, int block_size, float scale,
-                      void* stream) {
+int b200q_decode_attn_ex(const void* q, int q_stride, void* out, const void* kv_layer,
+                         const int32_t* block_table, int bt_stride, const int32_t* ctx_lens,
+                         int n_seqs, int n_q, int n_kv, int D, int block_size, float scale,
+                         float softcap, int window, void* stream) {
   B200Q_CHECK_ARG(n_seqs >= 0 && n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= 8,
                   "decode_attn: unsupported heads n_q=%d n_kv=%d (GQA group must be <= 8)", n_q,
                   n_kv);
-  B200Q_CHECK_ARG(block_size == 16 && (D == 64 || D == 128),
-                  "decode_attn: unsupported D=%d block_size=%d (D in {64,128}, block 16)", D,
+  B200Q_CHECK_ARG(block_size == 16 && (D == 64 || D == 128 || D == 256),
+                  "decode_attn: unsupported D=%d block_size=%d (D in {64,128,256}, block 16)", D,
                   block_size);
   if (n_seqs == 0) return B200Q_OK;
   cudaStream_t st = as_stream(stream);
@@ -722,37 +796,43 @@ int b200q_decode_attn(const void* q, int q_stride, void* out, const void* kv_lay
   const bool stream_variant =
       g_decode_variant >= 2 ||
       (g_decode_variant == 0 && (long long)n_seqs * n_kv >= 16LL * attn_num_sms());
-  if (stream_variant) {
-    if (D == 128)
-      return launch_decode_stream<128, 16>(q, q_stride, out, kv_layer, block_table, bt_stride,
-                                           ctx_lens, n_seqs, n_q, n_kv, scale, st);
-    return launch_decode_stream<64, 16>(q, q_stride, out, kv_layer, block_table, bt_stride,
-                                        ctx_lens, n_seqs, n_q, n_kv, scale, st);
-  }
-  if (D == 128)
-    return launch_decode<128, 16>(q, q_stride, out, kv_layer, block_table, bt_stride, ctx_lens,
-                                  n_seqs, n_q, n_kv, scale, st);
-  return launch_decode<64, 16>(q, q_stride, out, kv_layer, block_table, bt_stride, ctx_lens,
-                               n_seqs, n_q, n_kv, scale, st);
+  if (stream_variant)
+    B200Q_ATTN_DISPATCH(launch_decode_stream, q, q_stride, out, kv_layer, block_table, bt_stride,
+                        ctx_lens, n_seqs, n_q, n_kv, scale, softcap, window, st);
+  B200Q_ATTN_DISPATCH(launch_decode, q, q_stride, out, kv_layer, block_table, bt_stride, ctx_lens,
+                      n_seqs, n_q, n_kv, scale, softcap, window, st);
+}
+
+int b200q_decode_attn(const void* q, int q_stride, void* out, const void* kv_layer,
+                      const int32_t* block_table, int bt_stride, const int32_t* ctx_lens,
+                      int n_seqs, int n_q, int n_kv, int D, int block_size, float scale,
+                      void* stream) {
+  return b200q_decode_attn_ex(q, q_stride, out, kv_layer, block_table, bt_stride, ctx_lens, n_seqs,
+                              n_q, n_kv, D, block_size, scale, 0.f, 0, stream);
+}
+
+int b200q_prefill_attn_ex(const void* q, int q_stride, void* out, const void* kv_layer,
+                          const int32_t* block_table, int bt_stride, const int32_t* tiles,
+                          int n_tiles, int n_q, int n_kv, int D, int block_size, float scale,
+                          float softcap, int window, void* stream) {
+  B200Q_CHECK_ARG(n_tiles >= 0 && n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= 8,
+                  "prefill_attn: unsupported heads n_q=%d n_kv=%d (GQA group must be <= 8)", n_q,
+                  n_kv);
+  B200Q_CHECK_ARG(block_size == 16 && (D == 64 || D == 128 || D == 256),
+                  "prefill_attn: unsupported D=%d block_size=%d (D in {64,128,256}, block 16)", D,
+                  block_size);
+  if (n_tiles == 0) return B200Q_OK;
+  cudaStream_t st = as_stream(stream);
+  B200Q_ATTN_DISPATCH(launch_prefill, q, q_stride, out, kv_layer, block_table, bt_stride, tiles,
+                      n_tiles, n_q, n_kv, scale, softcap, window, st);
 }
 
 int b200q_prefill_attn(const void* q, int q_stride, void* out, const void* kv_layer,
                        const int32_t* block_table, int bt_stride, const int32_t* tiles,
                        int n_tiles, int n_q, int n_kv, int D, int block_size, float scale,
                        void* stream) {
-  B200Q_CHECK_ARG(n_tiles >= 0 && n_kv > 0 && n_q % n_kv == 0 && n_q / n_kv <= 8,
-                  "prefill_attn: unsupported heads n_q=%d n_kv=%d (GQA group must be <= 8)", n_q,
-                  n_kv);
-  B200Q_CHECK_ARG(block_size == 16 && (D == 64 || D == 128),
-                  "prefill_attn: unsupported D=%d block_size=%d (D in {64,128}, block 16)", D,
-                  block_size);
-  if (n_tiles == 0) return B200Q_OK;
-  cudaStream_t st = as_stream(stream);
-  if (D == 128)
-    return launch_prefill<128, 16>(q, q_stride, out, kv_layer, block_table, bt_stride, tiles,
-                                   n_tiles, n_q, n_kv, scale, st);
-  return launch_prefill<64, 16>(q, q_stride, out, kv_layer, block_table, bt_stride, tiles,
-                                n_tiles, n_q, n_kv, scale, st);
+  return b200q_prefill_attn_ex(q, q_stride, out, kv_layer, block_table, bt_stride, tiles, n_tiles,
+                               n_q, n_kv, D, block_size, scale, 0.f, 0, stream);
 }
 
 }  // extern "C"

@@ -38,6 +38,24 @@ __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ 
   }
 }
 
+// Gemma: out = bf16(table[id] * scale) (the normaliser sqrt(H), itself rounded to bf16 by the host)
+__global__ void __launch_bounds__(256) embed_scaled_kernel(const int32_t* __restrict__ ids,
+                                                           const uint4* __restrict__ table,
+                                                           uint4* __restrict__ out, int T, int chunks,
+                                                           float scale) {
+  long long total = (long long)T * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int t = (int)(i / chunks), c = (int)(i % chunks);
+    int id = __ldg(ids + t);
+    uint4 a = ld_nc_v4(table + (long long)id * chunks + c);
+    uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ap[k] = pack_bf16x2(bf16_lo(ap[k]) * scale, bf16_hi(ap[k]) * scale);
+    out[i] = a;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K2 RMSNorm / fused add + RMSNorm.  One 256-thread CTA per token row; the row lives in
 // registers between the reduction and the scale (one HBM read, one write per tensor).
@@ -106,6 +124,116 @@ __global__ void __launch_bounds__(NORM_THREADS)
       }
       st_v4(y + row * chunks + c, a);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Gemma-2 norms.  GemmaRMSNorm multiplies by (1 + w) and rounds ONCE:
+//   y = bf16( (x * rsqrt(mean(x^2) + eps)) * (1 + w) )      all in fp32 until the final cast.
+// gemma_norm_add_norm fuses the sandwich around a residual add (two row reductions, the row
+// stays in registers):  a = norm(x, w_post);  residual = bf16(residual + a);  x = norm(residual, w_next)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();  // red may still be read by the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_THREADS / 32; ++i) tot += red[i];
+  return tot;
+}
+
+__device__ __forceinline__ float chunk_sumsq(const uint4& a) {
+  const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float lo = bf16_lo(ap[k]), hi = bf16_hi(ap[k]);
+    ss += lo * lo + hi * hi;
+  }
+  return ss;
+}
+
+// a <- bf16((a * inv) * (1 + w))
+__device__ __forceinline__ void gemma_scale_chunk(uint4& a, const uint4& ww, float inv) {
+  uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(&ww);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float lo = (bf16_lo(ap[k]) * inv) * (1.f + bf16_lo(wp[k]));
+    float hi = (bf16_hi(ap[k]) * inv) * (1.f + bf16_hi(wp[k]));
+    ap[k] = pack_bf16x2(lo, hi);
+  }
+}
+
+template <bool kSandwich>
+__global__ void __launch_bounds__(NORM_THREADS)
+    gemma_norm_kernel(const uint4* __restrict__ x_in, uint4* __restrict__ residual,
+                      const uint4* __restrict__ w_post, const uint4* __restrict__ w_next,
+                      uint4* __restrict__ y, int chunks, float inv_h, float eps) {
+  __shared__ float red[NORM_THREADS / 32];
+  const long long row = blockIdx.x;
+  const uint4* xr = x_in + row * chunks;
+  uint4 v[NORM_MAX_CHUNKS];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < NORM_MAX_CHUNKS; ++j) {
+    int c = threadIdx.x + j * NORM_THREADS;
+    if (c < chunks) {
+      v[j] = ld_v4(xr + c);
+      ss += chunk_sumsq(v[j]);
+    }
+  }
+  float inv = __frsqrt_rn(block_sum_256(ss, red) * inv_h + eps);
+  if (kSandwich) {
+    // a = norm(x, w_post); residual <- bf16(residual + a); then the second norm over the new residual
+    ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NORM_MAX_CHUNKS; ++j) {
+      int c = threadIdx.x + j * NORM_THREADS;
+      if (c < chunks) {
+        uint4 a = v[j];
+        gemma_scale_chunk(a, __ldg(w_post + c), inv);
+        uint4 r = ld_v4(residual + row * chunks + c);
+        uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ap[k] = pack_bf16x2(bf16_lo(rp[k]) + bf16_lo(ap[k]), bf16_hi(rp[k]) + bf16_hi(ap[k]));
+        st_v4(residual + row * chunks + c, a);
+        v[j] = a;
+        ss += chunk_sumsq(a);
+      }
+    }
+    inv = __frsqrt_rn(block_sum_256(ss, red) * inv_h + eps);
+  }
+  const uint4* w_out = kSandwich ? w_next : w_post;
+#pragma unroll
+  for (int j = 0; j < NORM_MAX_CHUNKS; ++j) {
+    int c = threadIdx.x + j * NORM_THREADS;
+    if (c < chunks) {
+      uint4 a = v[j];
+      gemma_scale_chunk(a, __ldg(w_out + c), inv);
+      st_v4(y + row * chunks + c, a);
+    }
+  }
+}
+
+// final-logit soft-capping with every eager bf16 rounding: l <- bf16(bf16(tanh(bf16(l / cap))) * cap)
+__global__ void __launch_bounds__(256)
+    softcap_kernel(uint4* __restrict__ logits, long long n_chunks, float cap) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks;
+       i += (long long)gridDim.x * blockDim.x) {
+    uint4 a = ld_v4(logits + i);
+    uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float lo = round_bf16(tanhf(round_bf16(__fdiv_rn(bf16_lo(ap[k]), cap)))) * cap;
+      float hi = round_bf16(tanhf(round_bf16(__fdiv_rn(bf16_hi(ap[k]), cap)))) * cap;
+      ap[k] = pack_bf16x2(lo, hi);
+    }
+    st_v4(logits + i, a);
   }
 }
 
@@ -413,6 +541,51 @@ int b200q_embed(const int32_t* ids, const void* table, void* out, int T, int H, 
   return B200Q_OK;
 }
 
+int b200q_embed_scaled(const int32_t* ids, const void* table, void* out, int T, int H, float scale,
+                       void* stream) {
+  B200Q_CHECK_ARG(T >= 0 && H > 0 && H % 8 == 0, "embed_scaled: bad shape T=%d H=%d", T, H);
+  if (T == 0) return B200Q_OK;
+  int chunks = H / 8;
+  embed_scaled_kernel<<<grid_for((long long)T * chunks, 256), 256, 0, as_stream(stream)>>>(
+      ids, (const uint4*)table, (uint4*)out, T, chunks, scale);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
+int b200q_gemma_rmsnorm(const void* x, const void* w, void* y, int T, int H, float eps,
+                        void* stream) {
+  B200Q_CHECK_ARG(T >= 0 && H > 0 && H % 8 == 0 && H <= NORM_THREADS * NORM_MAX_CHUNKS * 8,
+                  "gemma_rmsnorm: bad shape T=%d H=%d", T, H);
+  if (T == 0) return B200Q_OK;
+  gemma_norm_kernel<false><<<T, NORM_THREADS, 0, as_stream(stream)>>>(
+      (const uint4*)x, nullptr, (const uint4*)w, nullptr, (uint4*)y, H / 8, 1.f / (float)H, eps);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
+int b200q_gemma_norm_add_norm(void* x, void* residual, const void* w_post, const void* w_next, int T,
+                              int H, float eps, void* stream) {
+  B200Q_CHECK_ARG(T >= 0 && H > 0 && H % 8 == 0 && H <= NORM_THREADS * NORM_MAX_CHUNKS * 8,
+                  "gemma_norm_add_norm: bad shape T=%d H=%d", T, H);
+  B200Q_CHECK_ARG(x && residual && w_post && w_next, "gemma_norm_add_norm: null argument");
+  if (T == 0) return B200Q_OK;
+  gemma_norm_kernel<true><<<T, NORM_THREADS, 0, as_stream(stream)>>>(
+      (const uint4*)x, (uint4*)residual, (const uint4*)w_post, (const uint4*)w_next, (uint4*)x, H / 8,
+      1.f / (float)H, eps);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
+int b200q_softcap_bf16(void* logits, int64_t n, float cap, void* stream) {
+  B200Q_CHECK_ARG(n >= 0 && n % 8 == 0 && cap > 0.f, "softcap: bad arguments n=%lld cap=%f",
+                  (long long)n, (double)cap);
+  B200Q_CHECK_ARG((reinterpret_cast<uintptr_t>(logits) & 15) == 0, "softcap: logits not 16-byte aligned");
+  if (n == 0) return B200Q_OK;
+  softcap_kernel<<<grid_for(n / 8, 256), 256, 0, as_stream(stream)>>>((uint4*)logits, n / 8, cap);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
 int b200q_rmsnorm(const void* x, const void* w, void* y, int T, int H, float eps, void* stream) {
   B200Q_CHECK_ARG(T >= 0 && H > 0 && H % 8 == 0 && H <= NORM_THREADS * NORM_MAX_CHUNKS * 8,
                   "rmsnorm: bad shape T=%d H=%d", T, H);
@@ -437,7 +610,7 @@ int b200q_add_rmsnorm(void* x, void* residual, const void* w, int T, int H, floa
 int b200q_rope_kvwrite(void* qkv, const void* cos_sin, const int32_t* positions,
                        const int32_t* slot_mapping, void* kv_layer, int T, int n_q, int n_kv,
                        int D, int block_size, void* stream) {
-  B200Q_CHECK_ARG(T >= 0 && (D == 64 || D == 128) && n_q > 0 && n_kv > 0 && block_size > 0,
+  B200Q_CHECK_ARG(T >= 0 && (D == 64 || D == 128 || D == 256) && n_q > 0 && n_kv > 0 && block_size > 0,
                   "rope_kvwrite: bad shape T=%d n_q=%d n_kv=%d D=%d bs=%d", T, n_q, n_kv, D,
                   block_size);
   if (T == 0) return B200Q_OK;

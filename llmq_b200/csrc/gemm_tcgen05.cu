@@ -123,13 +123,24 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 // [T, 2I] intermediate never touches HBM.
 constexpr int EPI_SMEM_PER_WARP = 32 * 128;  // 32 rows x 64 bf16
 
-template <int BN, bool kSwiGLU>
+// kAct: 0 = plain GEMM, 1 = SwiGLU (Llama), 2 = GeGLU with the tanh approximation (Gemma-2):
+// out = bf16(bf16(gelu_tanh(bf16(g))) * bf16(u)), gelu_tanh evaluated in fp32 like torch's kernel:
+// 0.5 * g * (1 + tanh(sqrt(2/pi) * (g + 0.044715 g^3)))
+constexpr int ACT_NONE = 0, ACT_SWIGLU = 1, ACT_GEGLU = 2;
+
+template <int BN, int kAct>
 __device__ __forceinline__ void epilogue_rows(uint32_t taddr, bf16* ctile, long long ldc,
                                               int row0, int M, uint8_t* patch, int lane) {
+  constexpr bool kSwiGLU = kAct != ACT_NONE;  // gated epilogue: tile = [gate (BN/2) | up (BN/2)]
   constexpr int OUT_BN = kSwiGLU ? BN / 2 : BN;
   auto act = [](uint32_t gb, uint32_t ub) -> float {
     const float g = round_bf16(__uint_as_float(gb)), u = round_bf16(__uint_as_float(ub));
-    return round_bf16(g / (1.f + __expf(-g))) * u;
+    if constexpr (kAct == ACT_GEGLU) {
+      const float inner = 0.7978845608028654f * (g + 0.044715f * (g * g * g));
+      return round_bf16(0.5f * g * (1.f + tanhf(inner))) * u;
+    } else {
+      return round_bf16(g / (1.f + __expf(-g))) * u;
+    }
   };
   const uint32_t patch_s = smem_u32(patch);
 #pragma unroll 1
@@ -184,11 +195,12 @@ __device__ __forceinline__ void epilogue_rows(uint32_t taddr, bf16* ctile, long 
   }
 }
 
-template <int BN, bool kSwiGLU = false>
+template <int BN, int kAct = ACT_NONE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b, bf16* __restrict__ C, int M,
                      int N, int K, int dbg, int splits, float* __restrict__ ws) {
+  constexpr bool kSwiGLU = kAct != ACT_NONE;
   // splits > 1 (split-K for decode-sized M, where a projection has too few output tiles to put
   // every SM on the weight stream): tile space = m x split x n, each CTA accumulates K/splits of
   // the reduction and writes an fp32 partial tile to ws[split][M][N]; splitk_reduce_kernel sums the
@@ -323,7 +335,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           }
         }
       } else if (!(dbg & 2)) {  // dbg&2: skip the drain (timing experiment)
-        epilogue_rows<BN, kSwiGLU>(taddr, ctile, ldc, row0, M, epi_smem + (warp - 2) * EPI_SMEM_PER_WARP, lane);
+        epilogue_rows<BN, kAct>(taddr, ctile, ldc, row0, M, epi_smem + (warp - 2) * EPI_SMEM_PER_WARP, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -448,11 +460,12 @@ __host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
          ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int BN, bool kSwiGLU = false>
+template <int BN, int kAct = ACT_NONE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b, bf16* __restrict__ C, int M,
                       int N, int K, int dbg) {
+  constexpr bool kSwiGLU = kAct != ACT_NONE;
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -572,7 +585,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       bf16* ctile = C + (long long)row0 * ldc + (long long)n_blk * OUT_BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
       if (!(dbg & 2))  // dbg&2: skip the drain (timing experiment)
-        epilogue_rows<BN, kSwiGLU>(taddr, ctile, ldc, row0, M, epi_smem + (warp - 2) * EPI_SMEM_PER_WARP, lane);
+        epilogue_rows<BN, kAct>(taddr, ctile, ldc, row0, M, epi_smem + (warp - 2) * EPI_SMEM_PER_WARP, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tmem_empty + acc, 0));
@@ -686,7 +699,7 @@ static int g_gemm_debug = 0;  // timing experiments only (wrong results): 1 = no
 static float* g_splitk_ws = nullptr;
 static size_t g_splitk_ws_bytes = 0;
 
-template <int BN, bool kSwiGLU = false>
+template <int BN, int kAct = ACT_NONE>
 static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int K,
                        cudaStream_t st, int splits = 1) {
   using Cfg = GemmCfg<BN>;
@@ -695,7 +708,7 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
   if (rc) return rc;
   rc = get_tmap(W, N, K, BN, &tb);
   if (rc) return rc;
-  auto kern = gemm_bf16_kernel<BN, kSwiGLU>;
+  auto kern = gemm_bf16_kernel<BN, kAct>;
   static bool attr_set = false;
   if (!attr_set) {
     B200Q_CUDA(
@@ -730,7 +743,7 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
 
 static int g_gemm2_pairs = 0;  // co-resident CTA pairs reported by the occupancy query
 
-template <int BN, bool kSwiGLU = false>
+template <int BN, int kAct = ACT_NONE>
 static int launch_gemm2(const void* A, const void* W, void* C, int M, int N, int K,
                         cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
@@ -739,7 +752,7 @@ static int launch_gemm2(const void* A, const void* W, void* C, int M, int N, int
   if (rc) return rc;
   rc = get_tmap(W, N, K, BN / 2, &tb);
   if (rc) return rc;
-  auto kern = gemm2_bf16_kernel<BN, kSwiGLU>;
+  auto kern = gemm2_bf16_kernel<BN, kAct>;
   static bool attr_set = false;
   if (!attr_set) {
     B200Q_CUDA(
@@ -797,6 +810,23 @@ int g_gemm_mode = 0;      // 0 = auto, 1 = force 1-CTA kernels, 2 = force the 2-
 }  // namespace b200q
 
 using namespace b200q;
+
+// shared body of the fused gate_up GEMMs (SwiGLU / GeGLU)
+template <int kAct>
+static int gemm_gated(const char* what, const void* A, const void* W, void* C, int M, int N, int K,
+                      void* stream) {
+  B200Q_CHECK_ARG(M >= 0 && N > 0 && K > 0 && K % GEMM_BK == 0 && N % 256 == 0,
+                  "%s: unsupported shape M=%d N=%d K=%d (need K%%64==0, N%%256==0)", what, M, N, K);
+  B200Q_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+                  "%s: operands must be 16-byte aligned", what);
+  if (M == 0) return B200Q_OK;
+  cudaStream_t st = as_stream(stream);
+  if ((g_gemm_mode == 2 && M > GEMM_BM) || (g_gemm_mode == 0 && prefer_2cta(M, N)))
+    return launch_gemm2<256, kAct>(A, W, C, M, N, K, st);
+  return launch_gemm<256, kAct>(A, W, C, M, N, K, st);
+}
 
 extern "C" {
 
@@ -905,17 +935,12 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
 // rows).  Same rounding points as b200q_gemm_bf16 followed by b200q_swiglu.
 int b200q_gemm_swiglu_bf16(const void* A, const void* W, void* C, int M, int N, int K,
                            void* stream) {
-  B200Q_CHECK_ARG(M >= 0 && N > 0 && K > 0 && K % GEMM_BK == 0 && N % 256 == 0,
-                  "gemm_swiglu: unsupported shape M=%d N=%d K=%d (need K%%64==0, N%%256==0)", M, N, K);
-  B200Q_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(C) & 15) == 0,
-                  "gemm_swiglu: operands must be 16-byte aligned");
-  if (M == 0) return B200Q_OK;
-  cudaStream_t st = as_stream(stream);
-  if ((g_gemm_mode == 2 && M > GEMM_BM) || (g_gemm_mode == 0 && prefer_2cta(M, N)))
-    return launch_gemm2<256, true>(A, W, C, M, N, K, st);
-  return launch_gemm<256, true>(A, W, C, M, N, K, st);
+  return gemm_gated<ACT_SWIGLU>("gemm_swiglu", A, W, C, M, N, K, stream);
+}
+
+// Gemma-2's GeGLU (gelu_tanh(gate) * up) in the same fused epilogue, same weight interleaving
+int b200q_gemm_geglu_bf16(const void* A, const void* W, void* C, int M, int N, int K, void* stream) {
+  return gemm_gated<ACT_GEGLU>("gemm_geglu", A, W, C, M, N, K, stream);
 }
 
 }  // extern "C"

@@ -2,6 +2,9 @@
 // token batch, composed from the op-level kernels.  Replaces GPUModelRunner.execute_model for
 // LlamaForCausalLM behind the reference worker (vllm/model_executor/models/llama.py:316-333,
 // 395-431): same layer wiring and rounding points, B200-native kernels.
+// B200Q_ARCH_GEMMA2 (vllm/model_executor/models/gemma2.py): same skeleton with
+// scaled embeddings, (1+w) sandwich norms around both residual adds, soft-capped attention with
+// alternating sliding-window layers, GeGLU, tied LM head and final-logit soft-capping.
 #include <string.h>
 
 #include <string>
@@ -15,9 +18,13 @@ struct b200q_layer {
   const void* input_norm = nullptr;
   const void* qkv = nullptr;
   const void* o = nullptr;
-  const void* post_norm = nullptr;
+  const void* post_norm = nullptr;  // llama: post_attention_layernorm (= the pre-MLP norm)
   const void* gate_up = nullptr;
   const void* down = nullptr;
+  // gemma2: the sandwich norms
+  const void* post_attn_norm = nullptr;
+  const void* pre_ffn_norm = nullptr;
+  const void* post_ffn_norm = nullptr;
 };
 
 struct b200q_model {
@@ -62,10 +69,20 @@ static int check_cfg(const b200q_model_config* c) {
   B200Q_CHECK_ARG(c != nullptr, "model config is null");
   B200Q_CHECK_ARG(c->hidden > 0 && c->hidden % 64 == 0 && c->hidden <= 8192,
                   "hidden=%d unsupported (multiple of 64, <= 8192)", c->hidden);
-  B200Q_CHECK_ARG(c->head_dim == 64 || c->head_dim == 128, "head_dim=%d unsupported", c->head_dim);
+  B200Q_CHECK_ARG(c->arch == B200Q_ARCH_LLAMA || c->arch == B200Q_ARCH_GEMMA2, "arch=%d unknown", c->arch);
+  B200Q_CHECK_ARG(c->head_dim == 64 || c->head_dim == 128 || c->head_dim == 256,
+                  "head_dim=%d unsupported (64, 128, 256)", c->head_dim);
   B200Q_CHECK_ARG(c->n_kv_heads > 0 && c->n_q_heads % c->n_kv_heads == 0 &&
-                      c->n_q_heads / c->n_kv_heads <= 8,
-                  "heads n_q=%d n_kv=%d unsupported", c->n_q_heads, c->n_kv_heads);
+                      c->n_q_heads / c->n_kv_heads <= (c->head_dim == 256 ? 4 : 8),
+                  "heads n_q=%d n_kv=%d unsupported (GQA group <= 8; <= 4 at head_dim 256)",
+                  c->n_q_heads, c->n_kv_heads);
+  B200Q_CHECK_ARG(c->sliding_window >= 0 && c->attn_softcap >= 0.f && c->final_softcap >= 0.f &&
+                      c->embed_scale >= 0.f,
+                  "negative sliding_window / softcap / embed_scale");
+  if (c->arch == B200Q_ARCH_LLAMA)
+    B200Q_CHECK_ARG(c->sliding_window == 0 && c->attn_softcap == 0.f && c->final_softcap == 0.f &&
+                        (c->embed_scale == 0.f || c->embed_scale == 1.f),
+                    "llama arch takes no sliding window / soft-capping / embedding scale");
   B200Q_CHECK_ARG(c->intermediate > 0 && c->intermediate % 128 == 0,
                   "intermediate=%d unsupported (multiple of 128: gate/up rows are interleaved in "
                   "128-row blocks for the fused SwiGLU epilogue)", c->intermediate);
@@ -149,6 +166,9 @@ int b200q_model_bind_weight(b200q_model_t m, const char* name, const void* p, in
     b200q_layer& L = m->layers[li];
     if (!strcmp(field, "input_norm")) { if ((rc = expect(1, H))) return rc; L.input_norm = p; return B200Q_OK; }
     if (!strcmp(field, "post_norm")) { if ((rc = expect(1, H))) return rc; L.post_norm = p; return B200Q_OK; }
+    if (!strcmp(field, "post_attn_norm")) { if ((rc = expect(1, H))) return rc; L.post_attn_norm = p; return B200Q_OK; }
+    if (!strcmp(field, "pre_ffn_norm")) { if ((rc = expect(1, H))) return rc; L.pre_ffn_norm = p; return B200Q_OK; }
+    if (!strcmp(field, "post_ffn_norm")) { if ((rc = expect(1, H))) return rc; L.post_ffn_norm = p; return B200Q_OK; }
     if (!strcmp(field, "qkv")) { if ((rc = expect(QKV, H))) return rc; L.qkv = p; return B200Q_OK; }
     if (!strcmp(field, "o")) { if ((rc = expect(H, QD))) return rc; L.o = p; return B200Q_OK; }
     if (!strcmp(field, "gate_up")) { if ((rc = expect(2 * I, H))) return rc; L.gate_up = p; return B200Q_OK; }
@@ -236,7 +256,10 @@ int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
   }
   for (int i = 0; i < c.n_layers; ++i) {
     const b200q_layer& L = m->layers[i];
-    if (!L.input_norm || !L.qkv || !L.o || !L.post_norm || !L.gate_up || !L.down) {
+    const bool norms_ok = c.arch == B200Q_ARCH_GEMMA2
+                              ? (L.post_attn_norm && L.pre_ffn_norm && L.post_ffn_norm)
+                              : L.post_norm != nullptr;
+    if (!L.input_norm || !L.qkv || !L.o || !norms_ok || !L.gate_up || !L.down) {
       set_error("forward: layer %d has unbound weights", i);
       return B200Q_ESTATE;
     }
@@ -270,35 +293,60 @@ int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
   } while (0)
   const double kv_tok_bytes = 2.0 * NKV * D * 2;  // K+V bytes per cached token per layer
 
-  B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_embed(b->token_ids, m->embed, m->residual, T, H, stream));
+  const bool gemma = c.arch == B200Q_ARCH_GEMMA2;
+  if (gemma && c.embed_scale > 0.f)
+    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_embed_scaled(b->token_ids, m->embed, m->residual, T, H, c.embed_scale, stream));
+  else
+    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_embed(b->token_ids, m->embed, m->residual, T, H, stream));
   for (int li = 0; li < c.n_layers; ++li) {
     const b200q_layer& L = m->layers[li];
     uint8_t* kv_layer = m->kv + li * kv_layer_bytes;
-    if (li == 0)
-      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_rmsnorm(m->residual, L.input_norm, m->x, T, H, c.rms_eps, stream));
-    else
+    // input norm.  llama: layer > 0 fuses the previous MLP's residual add; gemma2: layer > 0 got its
+    // normalised input from the previous layer's post-FFN sandwich kernel already
+    if (li == 0) {
+      if (gemma)
+        B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_gemma_rmsnorm(m->residual, L.input_norm, m->x, T, H, c.rms_eps, stream));
+      else
+        B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_rmsnorm(m->residual, L.input_norm, m->x, T, H, c.rms_eps, stream));
+    } else if (!gemma) {
       B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, L.input_norm, T, H, c.rms_eps, stream));
+    }
     B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * QKV * H, b200q_gemm_bf16(m->x, L.qkv, m->qkv, T, QKV, H, stream));
     B200Q_TRY(B200Q_PROF_ELEMENTWISE, (double)T * (QKV + QD + 2.0 * NKV * D) * 2, b200q_rope_kvwrite(m->qkv, m->rope, b->positions, b->slot_mapping, kv_layer, T, NQ,
                                  NKV, D, c.block_size, stream));
-    B200Q_TRY(B200Q_PROF_DECODE_ATTN, (double)b->sum_ctx_dec * kv_tok_bytes, b200q_decode_attn(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
+    // gemma2: even layers are the sliding-window ones (HF layer_types: sliding, full, sliding, ...)
+    const int window = (gemma && li % 2 == 0) ? c.sliding_window : 0;
+    B200Q_TRY(B200Q_PROF_DECODE_ATTN, (double)b->sum_ctx_dec * kv_tok_bytes, b200q_decode_attn_ex(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
                                 b->ctx_lens, b->n_dec, NQ, NKV, D, c.block_size, c.attn_scale,
-                                stream));
-    B200Q_TRY(B200Q_PROF_PREFILL_ATTN, (double)b->prefill_flops_per_layer, b200q_prefill_attn(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
+                                c.attn_softcap, window, stream));
+    B200Q_TRY(B200Q_PROF_PREFILL_ATTN, (double)b->prefill_flops_per_layer, b200q_prefill_attn_ex(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
                                  b->tiles, b->n_tiles, NQ, NKV, D, c.block_size, c.attn_scale,
-                                 stream));
+                                 c.attn_softcap, window, stream));
     B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * H * QD, b200q_gemm_bf16(m->attn, L.o, m->x, T, H, QD, stream));
-    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, L.post_norm, T, H, c.rms_eps, stream));
-    // gate_up GEMM with the SwiGLU fused into its epilogue (weights interleaved at bind time)
-    B200Q_TRY(B200Q_PROF_GEMM, 4.0 * T * I * H, b200q_gemm_swiglu_bf16(m->x, L.gate_up, m->act, T, 2 * I, H, stream));
+    if (gemma) {
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_gemma_norm_add_norm(m->x, m->residual, L.post_attn_norm, L.pre_ffn_norm, T, H, c.rms_eps, stream));
+      B200Q_TRY(B200Q_PROF_GEMM, 4.0 * T * I * H, b200q_gemm_geglu_bf16(m->x, L.gate_up, m->act, T, 2 * I, H, stream));
+    } else {
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, L.post_norm, T, H, c.rms_eps, stream));
+      // gate_up GEMM with the SwiGLU fused into its epilogue (weights interleaved at bind time)
+      B200Q_TRY(B200Q_PROF_GEMM, 4.0 * T * I * H, b200q_gemm_swiglu_bf16(m->x, L.gate_up, m->act, T, 2 * I, H, stream));
+    }
     B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * H * I, b200q_gemm_bf16(m->act, L.down, m->x, T, H, I, stream));
+    if (gemma && li + 1 < c.n_layers)
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_gemma_norm_add_norm(m->x, m->residual, L.post_ffn_norm, m->layers[li + 1].input_norm, T, H, c.rms_eps, stream));
   }
   if (b->n_sample > 0) {
-    // only the rows that sample need the final norm + LM head; add_rmsnorm runs on all rows
+    // only the rows that sample need the final norm + LM head; the fused add+norm runs on all rows
     // because x/residual are per-row anyway and the gather wants the normalised value.
-    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, m->final_norm, T, H, c.rms_eps, stream));
+    if (gemma)
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_gemma_norm_add_norm(m->x, m->residual, m->layers[c.n_layers - 1].post_ffn_norm, m->final_norm, T, H, c.rms_eps, stream));
+    else
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, m->final_norm, T, H, c.rms_eps, stream));
     B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * b->n_sample * H * 2, b200q_gather_rows(m->x, b->sample_rows, m->sel, b->n_sample, H, stream));
     B200Q_TRY(B200Q_PROF_GEMM, 2.0 * b->n_sample * (double)c.vocab * H, b200q_gemm_bf16(m->sel, m->lm_head, m->logits, b->n_sample, c.vocab, H, stream));
+    if (c.final_softcap > 0.f)
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * b->n_sample * c.vocab * 2,
+                b200q_softcap_bf16(m->logits, (int64_t)b->n_sample * c.vocab, c.final_softcap, stream));
     if (b->sample_params)
       B200Q_TRY(B200Q_PROF_ELEMENTWISE, (double)b->n_sample * c.vocab * 2,
                 b200q_sample_bf16(m->logits, b->sample_params, b->out_ids, b->n_sample, c.vocab, stream));

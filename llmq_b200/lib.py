@@ -39,7 +39,17 @@ class ModelConfig(C.Structure):
         ("tie_embeddings", C.c_int32),
         ("rms_eps", C.c_float),
         ("attn_scale", C.c_float),
+        # architecture extras (all zero = Llama)
+        ("arch", C.c_int32),
+        ("sliding_window", C.c_int32),
+        ("attn_softcap", C.c_float),
+        ("final_softcap", C.c_float),
+        ("embed_scale", C.c_float),
     ]
+
+
+ARCH_LLAMA = 0
+ARCH_GEMMA2 = 1
 
 
 class Batch(C.Structure):
@@ -121,6 +131,13 @@ SIGNATURES = {
     "b200q_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "b200q_argmax_bf16": (_i, [_vp, _vp, _i, _i, _vp]),
     "b200q_sample_bf16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "b200q_embed_scaled": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
+    "b200q_gemma_rmsnorm": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
+    "b200q_gemma_norm_add_norm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "b200q_decode_attn_ex": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _vp]),
+    "b200q_prefill_attn_ex": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _vp]),
+    "b200q_gemm_geglu_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200q_softcap_bf16": (_i, [_vp, _i64, _f, _vp]),
     "b200q_model_create": (_i, [C.POINTER(ModelConfig), C.POINTER(_vp)]),
     "b200q_model_destroy": (_i, [_vp]),
     "b200q_model_bind_weight": (_i, [_vp, C.c_char_p, _vp, _i64, _i64]),
@@ -222,16 +239,53 @@ def rope_kvwrite(qkv, cos_sin, positions, slot_mapping, kv_layer, n_q, n_kv, D, 
                                     qkv.shape[0], n_q, n_kv, D, block_size, _stream(stream)))
 
 
-def decode_attn(qkv, out, kv_layer, block_table, ctx_lens, n_q, n_kv, D, block_size, scale, stream=None):
+def decode_attn(qkv, out, kv_layer, block_table, ctx_lens, n_q, n_kv, D, block_size, scale, stream=None,
+                softcap: float = 0.0, window: int = 0):
+    if softcap or window:
+        check(load().b200q_decode_attn_ex(_p(qkv), qkv.shape[1], _p(out), _p(kv_layer), _p(block_table),
+                                          block_table.shape[1], _p(ctx_lens), ctx_lens.numel(), n_q, n_kv, D,
+                                          block_size, scale, softcap, window, _stream(stream)))
+        return
     check(load().b200q_decode_attn(_p(qkv), qkv.shape[1], _p(out), _p(kv_layer), _p(block_table),
                                    block_table.shape[1], _p(ctx_lens), ctx_lens.numel(), n_q, n_kv, D,
                                    block_size, scale, _stream(stream)))
 
 
-def prefill_attn(qkv, out, kv_layer, block_table, tiles, n_q, n_kv, D, block_size, scale, stream=None):
+def prefill_attn(qkv, out, kv_layer, block_table, tiles, n_q, n_kv, D, block_size, scale, stream=None,
+                 softcap: float = 0.0, window: int = 0):
+    if softcap or window:
+        check(load().b200q_prefill_attn_ex(_p(qkv), qkv.shape[1], _p(out), _p(kv_layer), _p(block_table),
+                                           block_table.shape[1], _p(tiles), tiles.shape[0], n_q, n_kv, D,
+                                           block_size, scale, softcap, window, _stream(stream)))
+        return
     check(load().b200q_prefill_attn(_p(qkv), qkv.shape[1], _p(out), _p(kv_layer), _p(block_table),
                                     block_table.shape[1], _p(tiles), tiles.shape[0], n_q, n_kv, D,
                                     block_size, scale, _stream(stream)))
+
+
+def embed_scaled(ids, table, out, scale, stream=None):
+    check(load().b200q_embed_scaled(_p(ids), _p(table), _p(out), ids.numel(), table.shape[1], scale, _stream(stream)))
+
+
+def gemma_rmsnorm(x, w, y, eps, stream=None):
+    check(load().b200q_gemma_rmsnorm(_p(x), _p(w), _p(y), x.shape[0], x.shape[1], eps, _stream(stream)))
+
+
+def gemma_norm_add_norm(x, residual, w_post, w_next, eps, stream=None):
+    """in place: residual <- bf16(residual + gemma_norm(x, w_post)); x <- gemma_norm(residual, w_next)"""
+    check(load().b200q_gemma_norm_add_norm(_p(x), _p(residual), _p(w_post), _p(w_next), x.shape[0], x.shape[1],
+                                           eps, _stream(stream)))
+
+
+def gemm_geglu_bf16(a, w_interleaved, c, stream=None):
+    M, K = a.shape
+    N = w_interleaved.shape[0]
+    assert w_interleaved.shape[1] == K and tuple(c.shape) == (M, N // 2)
+    check(load().b200q_gemm_geglu_bf16(_p(a), _p(w_interleaved), _p(c), M, N, K, _stream(stream)))
+
+
+def softcap_bf16(logits, cap, stream=None):
+    check(load().b200q_softcap_bf16(_p(logits), logits.numel(), cap, _stream(stream)))
 
 
 def gemm_bf16(a, w, c, stream=None):

@@ -38,12 +38,33 @@ class ModelSpec:
     eos_token_id: Optional[int] = None
     bos_token_id: Optional[int] = None
     name: str = "llama"
+    # architecture: "llama" (Llama / Mistral-style decoders) or "gemma2" 
+    arch: str = "llama"
+    query_pre_attn_scalar: Optional[float] = None  # gemma2: attention scale = this ** -0.5
+    attn_softcap: float = 0.0                      # gemma2: 50
+    final_softcap: float = 0.0                     # gemma2: 30
+    sliding_window: int = 0                        # gemma2: 4096 on the even layers
+
+    @property
+    def attn_scale(self) -> float:
+        return float(self.query_pre_attn_scalar or self.head_dim) ** -0.5
+
+    @property
+    def embed_scale(self) -> float:
+        """gemma2 multiplies the embeddings by sqrt(hidden), the factor itself rounded to bf16
+        (transformers Gemma2TextScaledWordEmbedding / vllm gemma2.py normalizer)"""
+        if self.arch != "gemma2":
+            return 0.0
+        return float(torch.tensor(self.hidden ** 0.5).to(torch.bfloat16))
 
     @staticmethod
     def from_hf_config(cfg: dict, name: str = "llama") -> "ModelSpec":
         arch = (cfg.get("architectures") or ["LlamaForCausalLM"])[0]
+        if arch == "Gemma2ForCausalLM":
+            return ModelSpec._from_gemma2_config(cfg, name)
         if arch not in ("LlamaForCausalLM", "MistralForCausalLM"):
-            raise ValueError(f"unsupported architecture {arch!r}: the b200 worker implements Llama-style decoders")
+            raise ValueError(f"unsupported architecture {arch!r}: the b200 worker implements Llama-style "
+                             "and Gemma-2 decoders")
         hd = cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"]
         rp = cfg.get("rope_parameters") if isinstance(cfg.get("rope_parameters"), dict) else None
         theta = cfg.get("rope_theta") or (rp or {}).get("rope_theta") or 10000.0
@@ -64,7 +85,47 @@ class ModelSpec:
             eos_token_id=eos, bos_token_id=cfg.get("bos_token_id"), name=name,
         )
 
+    @staticmethod
+    def _from_gemma2_config(cfg: dict, name: str) -> "ModelSpec":
+        if cfg.get("hidden_activation", cfg.get("hidden_act", "gelu_pytorch_tanh")) != "gelu_pytorch_tanh":
+            raise ValueError("gemma2: only hidden_activation=gelu_pytorch_tanh is implemented")
+        lt = cfg.get("layer_types")
+        if lt and any((t == "sliding_attention") != (i % 2 == 0) for i, t in enumerate(lt)):
+            raise ValueError("gemma2: only the stock layer pattern (even layers sliding) is implemented")
+        rp = cfg.get("rope_parameters") if isinstance(cfg.get("rope_parameters"), dict) else None
+        eos = cfg.get("eos_token_id")
+        if isinstance(eos, list):
+            eos = eos[0]
+        return ModelSpec(
+            hidden=cfg["hidden_size"], n_layers=cfg["num_hidden_layers"],
+            n_q_heads=cfg["num_attention_heads"], n_kv_heads=cfg["num_key_value_heads"],
+            head_dim=cfg["head_dim"], intermediate=cfg["intermediate_size"], vocab=cfg["vocab_size"],
+            rms_eps=cfg.get("rms_norm_eps", 1e-6),
+            rope_theta=float(cfg.get("rope_theta") or (rp or {}).get("rope_theta") or 10000.0),
+            rope_scaling=None, tie_embeddings=True,
+            max_position_embeddings=cfg.get("max_position_embeddings", 8192),
+            eos_token_id=eos, bos_token_id=cfg.get("bos_token_id"), name=name, arch="gemma2",
+            query_pre_attn_scalar=float(cfg.get("query_pre_attn_scalar", cfg["head_dim"])),
+            attn_softcap=float(cfg.get("attn_logit_softcapping") or 0.0),
+            final_softcap=float(cfg.get("final_logit_softcapping") or 0.0),
+            sliding_window=int(cfg.get("sliding_window") or 0))
+
     def to_hf_config(self) -> dict:
+        if self.arch == "gemma2":
+            return {
+                "architectures": ["Gemma2ForCausalLM"], "model_type": "gemma2",
+                "hidden_size": self.hidden, "num_hidden_layers": self.n_layers,
+                "num_attention_heads": self.n_q_heads, "num_key_value_heads": self.n_kv_heads,
+                "head_dim": self.head_dim, "intermediate_size": self.intermediate,
+                "vocab_size": self.vocab, "rms_norm_eps": self.rms_eps, "rope_theta": self.rope_theta,
+                "tie_word_embeddings": True, "max_position_embeddings": self.max_position_embeddings,
+                "hidden_activation": "gelu_pytorch_tanh", "attention_bias": False,
+                "query_pre_attn_scalar": self.query_pre_attn_scalar or self.head_dim,
+                "attn_logit_softcapping": self.attn_softcap or None,
+                "final_logit_softcapping": self.final_softcap or None,
+                "sliding_window": self.sliding_window or None, "torch_dtype": "bfloat16",
+                "bos_token_id": self.bos_token_id, "eos_token_id": self.eos_token_id,
+            }
         return {
             "architectures": ["LlamaForCausalLM"], "model_type": "llama",
             "hidden_size": self.hidden, "num_hidden_layers": self.n_layers,
@@ -103,7 +164,19 @@ LLAMA_32_1B = ModelSpec(hidden=2048, n_layers=16, n_q_heads=32, n_kv_heads=8, he
                                       "original_max_position_embeddings": 8192},
                         tie_embeddings=True, max_position_embeddings=131072, eos_token_id=128009,
                         bos_token_id=128000, name="llama-3.2-1b")
-BUILTIN_SPECS = {"llama-3-8b": LLAMA_3_8B, "llama-3.2-1b": LLAMA_32_1B}
+# google/gemma-2-9b(-it) and Unbabel/Tower-Plus-9B (BASELINE configs #4, #5) share this shape
+GEMMA_2_9B = ModelSpec(hidden=3584, n_layers=42, n_q_heads=16, n_kv_heads=8, head_dim=256,
+                       intermediate=14336, vocab=256000, rms_eps=1e-6, rope_theta=10000.0,
+                       tie_embeddings=True, max_position_embeddings=8192, eos_token_id=1,
+                       bos_token_id=2, name="gemma-2-9b", arch="gemma2", query_pre_attn_scalar=256.0,
+                       attn_softcap=50.0, final_softcap=30.0, sliding_window=4096)
+GEMMA_2_2B = ModelSpec(hidden=2304, n_layers=26, n_q_heads=8, n_kv_heads=4, head_dim=256,
+                       intermediate=9216, vocab=256000, rms_eps=1e-6, rope_theta=10000.0,
+                       tie_embeddings=True, max_position_embeddings=8192, eos_token_id=1,
+                       bos_token_id=2, name="gemma-2-2b", arch="gemma2", query_pre_attn_scalar=256.0,
+                       attn_softcap=50.0, final_softcap=30.0, sliding_window=4096)
+BUILTIN_SPECS = {"llama-3-8b": LLAMA_3_8B, "llama-3.2-1b": LLAMA_32_1B,
+                 "gemma-2-9b": GEMMA_2_9B, "gemma-2-2b": GEMMA_2_2B}
 
 
 def rope_table(max_pos: int, head_dim: int, theta: float, scaling: Optional[dict]) -> torch.Tensor:
@@ -143,7 +216,12 @@ def fuse_hf_weights(spec: ModelSpec, sd: Dict[str, torch.Tensor]) -> Iterable[Tu
     for i in range(spec.n_layers):
         p = f"model.layers.{i}."
         yield f"layers.{i}.input_norm", sd[p + "input_layernorm.weight"].reshape(1, -1)
-        yield f"layers.{i}.post_norm", sd[p + "post_attention_layernorm.weight"].reshape(1, -1)
+        if spec.arch == "gemma2":
+            yield f"layers.{i}.post_attn_norm", sd[p + "post_attention_layernorm.weight"].reshape(1, -1)
+            yield f"layers.{i}.pre_ffn_norm", sd[p + "pre_feedforward_layernorm.weight"].reshape(1, -1)
+            yield f"layers.{i}.post_ffn_norm", sd[p + "post_feedforward_layernorm.weight"].reshape(1, -1)
+        else:
+            yield f"layers.{i}.post_norm", sd[p + "post_attention_layernorm.weight"].reshape(1, -1)
         yield f"layers.{i}.qkv", torch.cat([sd[p + "self_attn.q_proj.weight"],
                                             sd[p + "self_attn.k_proj.weight"],
                                             sd[p + "self_attn.v_proj.weight"]], 0)
@@ -161,14 +239,20 @@ def random_engine_weights(spec: ModelSpec, seed: int, device, std: float = 0.02)
     def mat(r, c):
         return (torch.randn(r, c, generator=g, device=device, dtype=torch.float32) * std).to(torch.bfloat16)
 
-    ones = lambda: torch.ones(1, spec.hidden, dtype=torch.bfloat16, device=device)
+    gemma = spec.arch == "gemma2"
+    # unit norm scale: w = 1 for Llama's x*w, w = 0 for Gemma's x*(1+w)
+    ones = lambda: torch.full((1, spec.hidden), 0.0 if gemma else 1.0, dtype=torch.bfloat16, device=device)
     yield "embed", mat(spec.vocab, spec.hidden)
     yield "final_norm", ones()
     if not spec.tie_embeddings:
         yield "lm_head", mat(spec.vocab, spec.hidden)
     for i in range(spec.n_layers):
         yield f"layers.{i}.input_norm", ones()
-        yield f"layers.{i}.post_norm", ones()
+        if gemma:
+            for n in ("post_attn_norm", "pre_ffn_norm", "post_ffn_norm"):
+                yield f"layers.{i}.{n}", ones()
+        else:
+            yield f"layers.{i}.post_norm", ones()
         yield f"layers.{i}.qkv", mat(spec.qkv_dim, spec.hidden)
         yield f"layers.{i}.o", mat(spec.hidden, spec.n_q_heads * spec.head_dim)
         yield f"layers.{i}.gate_up", mat(2 * spec.intermediate, spec.hidden)
@@ -222,7 +306,10 @@ class NativeModel:
             n_kv_heads=spec.n_kv_heads, head_dim=spec.head_dim, intermediate=spec.intermediate,
             vocab=spec.vocab, block_size=BLOCK_SIZE, max_tokens=max_tokens, max_seqs=max_seqs,
             max_pos=self.max_model_len, tie_embeddings=int(spec.tie_embeddings),
-            rms_eps=spec.rms_eps, attn_scale=spec.head_dim ** -0.5)
+            rms_eps=spec.rms_eps, attn_scale=spec.attn_scale,
+            arch=L.ARCH_GEMMA2 if spec.arch == "gemma2" else L.ARCH_LLAMA,
+            sliding_window=spec.sliding_window, attn_softcap=spec.attn_softcap,
+            final_softcap=spec.final_softcap, embed_scale=spec.embed_scale)
         h = C.c_void_p()
         L.check(self.lib.b200q_model_create(C.byref(self.cfg), C.byref(h)))
         self.handle = h

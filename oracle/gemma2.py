@@ -1,7 +1,8 @@
 """oracle/gemma2.py — CPU restatement of the Gemma-2 architecture (the next model
 family; BASELINE configs #4 Tower-Plus-9B and #5 Gemma-2-9B-it are Gemma-2-shaped).
-TEST INFRASTRUCTURE ONLY (see oracle/ops.py).  Round-1 status: oracle + goldens only — the CUDA
-engine does not implement this architecture yet; this file is the parity target for it.
+TEST INFRASTRUCTURE ONLY (see oracle/ops.py).  Parity target of the B200Q_ARCH_GEMMA2 path of
+libb200q (tests/test_gemma2_gpu.py); pinned against transformers' Gemma2ForCausalLM goldens
+(tests/test_oracle_golden.py).
 
 Follows vllm/model_executor/models/gemma2.py, i.e. transformers' Gemma2 (modeling_gemma2.py):
   * embeddings scaled by sqrt(hidden) (scale cast to the weight dtype)           :349-360
@@ -134,18 +135,20 @@ class Gemma2Oracle:
             logits = _r(_r(torch.tanh(_r(logits / c, mode)), mode) * c, mode)
         return logits, kv
 
-    def greedy(self, prompt_ids: List[int], max_new_tokens: int):
+    def greedy(self, prompt_ids: List[int], max_new_tokens: int, return_logits: bool = False):
         ids = torch.tensor(prompt_ids, dtype=torch.int64)
         logits, kv = self.forward(ids, torch.arange(len(prompt_ids)), None, all_logits=False)
-        out = []
+        out, lg = [], []
         for _ in range(max_new_tokens):
             t = int(ops.argmax_first(logits[-1:])[0])
             out.append(t)
+            if return_logits:
+                lg.append(logits[-1].clone())
             if len(out) == max_new_tokens:
                 break
             pos = len(prompt_ids) + len(out) - 1
             logits, kv = self.forward(torch.tensor([t]), torch.tensor([pos]), kv, all_logits=False)
-        return out
+        return (out, lg) if return_logits else out
 
 
 def random_gemma2_weights(d: Gemma2Dims, seed: int = 1234, std: float = 0.02, dtype=torch.bfloat16):

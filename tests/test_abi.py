@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(handle, s), f"{s} declared in b200q.h but not exported by libb200q.so"
         assert s in lib.SIGNATURES, f"{s} has no ctypes signature in llmq_b200/lib.py"
-    assert handle.b200q_version() == 1
+    m = re.search(r"#define B200Q_VERSION (\d+)", open(HEADER).read())
+    assert handle.b200q_version() == int(m.group(1))
 
 
 def test_header_is_plain_c_and_struct_layouts_match(tmp_path):

@@ -71,7 +71,7 @@ def test_swiglu(cuda, T, I):
     bf16_close(out, O.swiglu(gu.float()), what="swiglu", max_mismatch_frac=0.03)
 
 
-@pytest.mark.parametrize("D,n_q,n_kv", [(128, 32, 8), (64, 32, 8), (128, 4, 1)])
+@pytest.mark.parametrize("D,n_q,n_kv", [(128, 32, 8), (64, 32, 8), (128, 4, 1), (256, 16, 8), (256, 8, 4)])
 def test_rope_kvwrite(cuda, D, n_q, n_kv):
     from llmq_b200 import lib
     T, BS, NB, max_pos = 37, 16, 12, 512

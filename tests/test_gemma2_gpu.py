@@ -44,9 +44,12 @@ def test_gemma_norm_add_norm(cuda, T, H):
     a = gemma_rms_norm(x.float(), w1.float(), 1e-6, "bf16")
     r_ref = (r.float() + a).to(BF).float()
     y_ref = gemma_rms_norm(r_ref, w2.float(), 1e-6, "bf16")
-    # the first norm may flip a few roundings (reduction order); they propagate 1:1 into the residual
-    bf16_close(rg, r_ref, what="norm_add_norm residual")
-    bf16_close(xg, y_ref, ulps=2.0, what="norm_add_norm output")
+    # the first norm can flip the rounding of a handful of elements (reduction order: ~1e-5 of them);
+    # such a flip is one bf16 ulp of `a` (|a| up to ~4), which enters the residual and the second norm
+    # 1:1 — hence the absolute term; max_mismatch_frac keeps the check tight (<= 0.1 % differ at all)
+    ulp_a = 2.0 ** -7 * a.abs().max().item()
+    bf16_close(rg, r_ref, atol=ulp_a, max_mismatch_frac=0.001, what="norm_add_norm residual")
+    bf16_close(xg, y_ref, ulps=2.0, atol=2 * ulp_a, what="norm_add_norm output")
 
 
 def test_embed_scaled_and_softcap(cuda):

@@ -252,11 +252,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def builtin_weight_gb(model_key: str) -> float:
+    from llmq_b200.model import BUILTIN_SPECS
+    return BUILTIN_SPECS[model_key].weight_bytes_per_step() / 1e9
+
+
 def workload_config(args, per_gpu_jobs):
     return {"workload": f"{args.model} random-init bf16, {args.prompt_tokens}-in/{args.out_tokens}-out greedy, "
                         f"{per_gpu_jobs} jobs per step per GPU, queue-sharded (job i -> rank i % N)",
             "max_num_seqs": args.max_num_seqs, "max_num_batched_tokens": args.max_num_batched_tokens,
-            "gpu_memory_utilization": args.gpu_memory_utilization, "kv_block_size": 16, "l2": "working set per step (weights 15 GB + KV) >> 126 MB L2, no flush needed",
+            "gpu_memory_utilization": args.gpu_memory_utilization, "kv_block_size": 16, "l2": f"working set per step (weights {builtin_weight_gb(args.model):.0f} GB + KV) >> 126 MB L2, no flush needed",
             "parallelism": f"dp{args.gpus} (independent replicas, no collective)"}
 
 
@@ -432,8 +437,9 @@ def run_native(args):
                 "traffic": None, "peak_source": peaks["source"],
                 "launch_avg_ms": round(g["ms"] / max(g["launches"], 1), 5), "launches": g["launches"],
                 "share_of_device_time": shares}
-    roofline["traffic"], roofline["traffic_note"] = ncu_traffic("gemm_bf16_kernel<256, 1>")
-    roofline_dec = {"bound": "hbm", "kernel": "b200q::decode_attn_stream_kernel<128,16> (B*n_kv >= 16*SMs) / decode_attn_kernel", "achieved": round(dec_gbs, 1),
+    if args.model == "llama-3-8b":  # the committed ncu capture is of this model's fused gate_up GEMM
+        roofline["traffic"], roofline["traffic_note"] = ncu_traffic("gemm_bf16_kernel<256, 1>")
+    roofline_dec = {"bound": "hbm", "kernel": f"b200q::decode_attn_stream_kernel<{spec.head_dim},16> (B*n_kv >= 16*SMs) / decode_attn_kernel", "achieved": round(dec_gbs, 1),
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(dec_gbs / peaks["hbm_gbs"], 4),
                     "launch_avg_ms": round(d["ms"] / max(d["launches"], 1), 5), "launches": d["launches"]}
     # whole-step decode HBM roofline fraction: algorithmic bytes per output token

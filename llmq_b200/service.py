@@ -20,15 +20,62 @@ from . import lib as L
 
 
 class _Req:
-    __slots__ = ("rid", "prompt_ids", "max_new", "stop", "future", "out_ids", "text_len", "loop",
+    __slots__ = ("slot", "prompt_ids", "max_new", "stop", "future", "text_len", "loop",
                  "temperature", "seed")
 
-    def __init__(self, rid, prompt_ids, max_new, stop, future, loop, temperature=0.0, seed=0):
-        self.rid, self.prompt_ids, self.max_new, self.stop = rid, prompt_ids, max_new, stop
+    def __init__(self, prompt_ids, max_new, stop, future, loop, temperature=0.0, seed=0):
+        self.prompt_ids, self.max_new, self.stop = prompt_ids, max_new, stop
         self.future, self.loop = future, loop
         self.temperature, self.seed = temperature, seed
-        self.out_ids: List[int] = []
+        self.slot = -1   # engine request id = row of the token table, assigned on the engine thread
         self.text_len = 0
+
+
+class _TokenTable:
+    """Generated tokens of the live requests as one int32 matrix (row = request slot = the engine's
+    request id), so that a step's (ids, tokens) arrays are stored with two vectorised numpy
+    operations instead of a Python loop over the batch: with thousands of sequences per step that
+    loop sits between two GPU steps and idles the device (host fast path)."""
+
+    def __init__(self):
+        import numpy as np
+
+        self.np = np
+        self.tok = np.empty((0, 0), dtype=np.int32)
+        self.n = np.zeros(0, dtype=np.int64)
+        self.has_stop = np.zeros(0, dtype=bool)
+        self.free: List[int] = []
+
+    def alloc(self, max_new: int, has_stop: bool) -> int:
+        np = self.np
+        rows, width = self.tok.shape
+        if not self.free or max_new > width:
+            new_rows = rows if self.free else max(64, rows * 2)
+            new_width = max(width, max_new)
+            tok = np.empty((new_rows, new_width), dtype=np.int32)  # untouched pages cost nothing
+            tok[:rows, :width] = self.tok
+            self.tok = tok
+            if new_rows > rows:
+                self.n = np.concatenate([self.n, np.zeros(new_rows - rows, dtype=np.int64)])
+                self.has_stop = np.concatenate([self.has_stop, np.zeros(new_rows - rows, dtype=bool)])
+                self.free.extend(range(new_rows - 1, rows - 1, -1))
+        slot = self.free.pop()
+        self.n[slot] = 0
+        self.has_stop[slot] = has_stop
+        return slot
+
+    def release(self, slot: int) -> None:
+        self.has_stop[slot] = False
+        self.free.append(slot)
+
+    def append_step(self, slots, toks) -> None:
+        """one token for each of `slots` (unique within a step)"""
+        n = self.n[slots]
+        self.tok[slots, n] = toks
+        self.n[slots] = n + 1
+
+    def tokens(self, slot: int) -> List[int]:
+        return self.tok[slot, : self.n[slot]].tolist()
 
 
 class GenerationService:
@@ -40,7 +87,8 @@ class GenerationService:
         self.tokenizer = tokenizer
         self.eos_token_id = eos_token_id
         self._inbox: "queue.SimpleQueue[_Req]" = queue.SimpleQueue()
-        self._reqs: Dict[int, _Req] = {}
+        self._reqs: Dict[int, _Req] = {}   # by slot; touched only on the engine thread
+        self._table = _TokenTable()
         self._next_id = 0
         # B200Q_SEED pins the per-request streams (reproducible runs); default: fresh entropy
         env_seed = os.environ.get("B200Q_SEED")
@@ -54,6 +102,12 @@ class GenerationService:
         self.last_finish_t: Optional[float] = None
 
     def start(self):
+        # The engine thread re-acquires the GIL after every device step; a busy event-loop thread
+        # (tokenising, pydantic) hands it over only at the interpreter's switch interval, 5 ms by
+        # default — comparable to a whole step of a small model.  0.2 ms bounds that wait.
+        import sys
+
+        sys.setswitchinterval(min(sys.getswitchinterval(), 2e-4))
         self._thread.start()
 
     def stop(self):
@@ -69,37 +123,54 @@ class GenerationService:
         seed None = a fresh stream per request (unseeded, like the reference)."""
         if self.error is not None:
             raise RuntimeError(f"engine thread died: {self.error!r}")
+        import numpy as np
+
         fut = loop.create_future()
+        # int32 array built here, on the caller's thread: the engine thread only passes its pointer on
+        prompt_ids = np.ascontiguousarray(prompt_ids, dtype=np.int32)
         self._next_id += 1
         if seed is None:
             seed = (self._base_seed + 0x9E3779B97F4A7C15 * self._next_id) & 0xFFFFFFFFFFFFFFFF
-        self._inbox.put(_Req(self._next_id, prompt_ids, max_new, stop, fut, loop, temperature, seed))
+        self._inbox.put(_Req(prompt_ids, max_new, stop, fut, loop, temperature, seed))
         return fut
 
     # ---- engine thread ----
     def _finish(self, batch, r: _Req, text: Optional[str] = None, exc: Optional[BaseException] = None):
-        self._reqs.pop(r.rid, None)
-        if exc is None and text is None:
-            text = self.tokenizer.decode(r.out_ids, skip_special_tokens=True)
+        n_out = 0
+        if r.slot >= 0:
+            self._reqs.pop(r.slot, None)
+            n_out = int(self._table.n[r.slot])
+            if exc is None and text is None:
+                # hand the ids over; detokenisation happens in _deliver on the caller's loop thread,
+                # concurrently with the next device step instead of between two steps
+                text = self._table.tokens(r.slot)
+            self._table.release(r.slot)
+            r.slot = -1
         self.jobs_done += 1
-        self.tokens_out += len(r.out_ids)
+        self.tokens_out += n_out
         self.last_finish_t = time.perf_counter()
-        batch.setdefault(r.loop, []).append((r.future, text, exc, len(r.out_ids)))
+        batch.setdefault(r.loop, []).append((r.future, text, exc, n_out))
 
-    @staticmethod
-    def _deliver(items):
+    def _deliver(self, items):
+        """runs on the event-loop thread of the requests in `items`; `text` is either the final
+        string (stop-string cut) or the generated ids still to be detokenised"""
         for fut, text, exc, n in items:
             if fut.done():
                 continue
             if exc is not None:
                 fut.set_exception(exc)
-            else:
+                continue
+            try:
+                if not isinstance(text, str):
+                    text = self.tokenizer.decode(text, skip_special_tokens=True)
                 fut.set_result((text, n))
+            except Exception as e:  # a detokeniser failure must not strand the waiter
+                fut.set_exception(e)
 
     def _check_stop_strings(self, r: _Req) -> Optional[str]:
         """vLLM detokenizer semantics (vllm/v1/engine/detokenizer.py:131-143): after every new
         token look for a stop string in the newly produced text; the output is cut before it."""
-        text = self.tokenizer.decode(r.out_ids, skip_special_tokens=True)
+        text = self.tokenizer.decode(self._table.tokens(r.slot), skip_special_tokens=True)
         start = max(0, r.text_len - max(len(s) for s in r.stop))
         r.text_len = len(text)
         best = -1
@@ -125,10 +196,11 @@ class GenerationService:
                     while True:
                         if self.first_submit_t is None:
                             self.first_submit_t = time.perf_counter()
+                        r.slot = self._table.alloc(max(int(r.max_new), 1), bool(r.stop))
                         try:
-                            eng.add_request(r.rid, r.prompt_ids, r.max_new, ignore_eos=False,
+                            eng.add_request(r.slot, r.prompt_ids, r.max_new, ignore_eos=False,
                                             temperature=r.temperature, seed=r.seed)
-                            self._reqs[r.rid] = r
+                            self._reqs[r.slot] = r
                         except ValueError as e:  # un-servable job => dropped by the base class
                             self._finish(batch, r, exc=e)
                         r = self._inbox.get_nowait()
@@ -136,20 +208,23 @@ class GenerationService:
                     pass
                 if eng.has_work():
                     ids, toks, flags = eng.step()
-                    for rid, tok, flag in zip(ids.tolist(), toks.tolist(), flags.tolist()):
-                        r = self._reqs.get(rid)
-                        if r is None:
-                            continue
-                        r.out_ids.append(tok)
-                        if r.stop:
+                    table = self._table
+                    table.append_step(ids, toks)  # vectorised: no per-token Python work
+                    # per-request work only for the few that carry stop strings or finished this step
+                    stop_hit = set()
+                    if table.has_stop.any():
+                        for slot, flag in zip(ids[table.has_stop[ids]].tolist(),
+                                              flags[table.has_stop[ids]].tolist()):
+                            r = self._reqs[slot]
                             cut = self._check_stop_strings(r)
                             if cut is not None:
                                 if not flag:
-                                    eng.abort(rid)
+                                    eng.abort(slot)
+                                stop_hit.add(slot)
                                 self._finish(batch, r, text=cut)
-                                continue
-                        if flag:
-                            self._finish(batch, r)
+                    for slot in ids[flags != 0].tolist():
+                        if slot not in stop_hit:
+                            self._finish(batch, self._reqs[slot])
                 for loop, items in batch.items():
                     loop.call_soon_threadsafe(self._deliver, items)
         except BaseException as e:  # surface engine failures to every waiter

@@ -215,7 +215,9 @@ class GenerationService:
                     if table.has_stop.any():
                         for slot, flag in zip(ids[table.has_stop[ids]].tolist(),
                                               flags[table.has_stop[ids]].tolist()):
-                            r = self._reqs[slot]
+                            r = self._reqs.get(slot)
+                            if r is None:
+                                continue
                             cut = self._check_stop_strings(r)
                             if cut is not None:
                                 if not flag:
@@ -223,8 +225,9 @@ class GenerationService:
                                 stop_hit.add(slot)
                                 self._finish(batch, r, text=cut)
                     for slot in ids[flags != 0].tolist():
-                        if slot not in stop_hit:
-                            self._finish(batch, self._reqs[slot])
+                        r = self._reqs.get(slot)
+                        if r is not None and slot not in stop_hit:
+                            self._finish(batch, r)
                 for loop, items in batch.items():
                     loop.call_soon_threadsafe(self._deliver, items)
         except BaseException as e:  # surface engine failures to every waiter

@@ -131,3 +131,80 @@ def write_jobs_jsonl(path: str, n_jobs: int, vocab_size: int, prompt_tokens: int
         for j in make_jobs(n_jobs, vocab_size, prompt_tokens, seed):
             f.write(json.dumps(j) + "\n")
     return path
+
+
+class _NoDeviceModel:
+    """stands where Engine.model is: no CUDA device, nothing to close"""
+    device = None
+
+    def __init__(self, max_model_len: int):
+        self.max_model_len = max_model_len
+
+    def close(self):
+        pass
+
+
+class DryRunEngine:
+    """llmq_b200.model.Engine's call surface over `b200q_engine_create_dryrun`: the real C++
+    scheduler, paged-KV block manager and per-step metadata packing, no model and no CUDA; every
+    "sampled" token is (previous token + 1) mod vocab.  For host-logic tests and
+    tools/host_path_bench.py only — it cannot generate text from a model and the worker never
+    constructs it.  `step_ms` stands in for the device time of a step (sleep, GIL released)."""
+
+    def __init__(self, vocab: int, max_num_seqs: int, max_num_batched_tokens: int, max_model_len: int,
+                 num_blocks: int, eos_token_id: Optional[int] = None, policy: int = 1, step_ms: float = 0.0):
+        import ctypes as C
+
+        from . import lib as L
+
+        self._C, self._L = C, L
+        self.lib = L.load()
+        cfg = L.EngineConfig(max_num_seqs=max_num_seqs, max_num_batched_tokens=max_num_batched_tokens,
+                             max_model_len=max_model_len,
+                             eos_token_id=-1 if eos_token_id is None else int(eos_token_id), policy=policy)
+        h = C.c_void_p()
+        L.check(self.lib.b200q_engine_create_dryrun(C.byref(cfg), vocab, 16, num_blocks, C.byref(h)))
+        self.handle, self.cap = h, max_num_seqs
+        self._ids = np.zeros(self.cap, np.int64)
+        self._tok = np.zeros(self.cap, np.int32)
+        self._flg = np.zeros(self.cap, np.int32)
+        self.model = _NoDeviceModel(max_model_len)
+        self.step_s = step_ms / 1e3
+        self.steps = 0
+
+    def add_request(self, req_id, prompt_ids, max_new_tokens, ignore_eos=False, temperature=0.0, seed=0):
+        arr = np.ascontiguousarray(prompt_ids, dtype=np.int32)
+        rc = self.lib.b200q_engine_add_request(self.handle, int(req_id), arr.ctypes.data, arr.size,
+                                               int(max_new_tokens), int(ignore_eos))
+        if rc == -1:
+            raise ValueError(self.lib.b200q_last_error().decode())
+        self._L.check(rc)
+
+    def abort(self, req_id):
+        self._L.check(self.lib.b200q_engine_abort(self.handle, int(req_id)))
+
+    def has_work(self) -> bool:
+        return bool(self.lib.b200q_engine_has_work(self.handle))
+
+    def step(self):
+        n = self._C.c_int32(0)
+        self._L.check(self.lib.b200q_engine_step(self.handle, self._ids.ctypes.data, self._tok.ctypes.data,
+                                                 self._flg.ctypes.data, self.cap, self._C.byref(n)))
+        if self.step_s:
+            import time
+
+            time.sleep(self.step_s)
+        self.steps += 1
+        k = n.value
+        return self._ids[:k], self._tok[:k], self._flg[:k]
+
+    def stats(self):
+        s = self._L.EngineStats()
+        self._L.check(self.lib.b200q_engine_get_stats(self.handle, self._C.byref(s)))
+        return s
+
+    def close(self):
+        if self.handle:
+            self.lib.b200q_engine_destroy(self.handle)
+            self.handle = None
+

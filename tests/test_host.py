@@ -237,3 +237,71 @@ def test_cli_install_routes_the_vllm_slot_to_the_native_worker():
     assert mod.VLLMWorker is B200Worker
     from llmq.cli import main as M
     assert "b200" in M.worker.commands and "run" in M.worker.commands
+
+
+def test_service_over_the_real_cpp_scheduler_dryrun(monkeypatch):
+    """B200Worker + GenerationService on the REAL C++ engine in dry-run mode (scheduler, paged-KV
+    block manager, chunked prefill, preemption — no GPU; token = previous + 1): ragged prompts,
+    per-job max_tokens, a stop string and a KV pool small enough to force preemptions must still
+    give every job exactly its own continuation, through the reference's BaseWorker and broker."""
+    from llmq_b200.fixtures import DryRunEngine
+
+    aio_pika.reset_brokers()
+    tok = build_tokenizer(VOCAB)
+    made = {}
+
+    def dry_build_service(model_name, **kw):
+        eng = DryRunEngine(VOCAB, max_num_seqs=12, max_num_batched_tokens=48, max_model_len=96,
+                           num_blocks=30, eos_token_id=None, policy=1)
+        made["engine"] = eng
+        return S.GenerationService(eng, tok, None)
+
+    import llmq_b200.worker as W
+    monkeypatch.setattr(W, "build_service", dry_build_service)
+    monkeypatch.setenv("VLLM_MAX_TOKENS", "20")
+    monkeypatch.setenv("VLLM_QUEUE_PREFETCH", "64")
+    monkeypatch.setenv("B200Q_TEMPERATURE", "0")
+    import numpy as np
+    rng = np.random.default_rng(3)
+    specs = []  # (id, last word, n_prompt_words, max_tokens or None)
+    for i in range(60):
+        n = int(rng.integers(1, 60))
+        specs.append((f"d{i}", int(rng.integers(10, 900)), n, None if i % 3 else int(rng.integers(1, 20))))
+
+    async def main():
+        w = B200Worker("random:dry", "dq2", tensor_parallel_size=1)
+        task = asyncio.create_task(w.run())
+        b = BrokerManager()
+        await b.connect()
+        await b.setup_queue_infrastructure("dq2")
+        for jid, last, n, cap in specs:
+            words = ["w5"] * (n - 1) + [f"w{last}"]
+            extra = {} if cap is None else {"max_tokens": cap}
+            await b.publish_job("dq2", Job(id=jid, prompt=" ".join(words), **extra))
+        await b.publish_job("dq2", Job(id="stop", prompt="w100", stop=["w104"]))
+        got = {}
+
+        async def on_res(m):
+            r = Result.parse_raw(m.body)
+            got[r.id] = r.result
+            await m.ack()
+
+        await b.consume_results("dq2", on_res)
+        for _ in range(400):
+            if len(got) == len(specs) + 1:
+                break
+            await asyncio.sleep(0.05)
+        st = made["engine"].stats()  # before cleanup destroys the engine
+        made["preemptions"], made["blocks"] = st.preemptions, (st.free_blocks, st.total_blocks)
+        w.running = False
+        await asyncio.wait_for(task, 10)
+        return got
+
+    got = asyncio.run(main())
+    assert len(got) == len(specs) + 1
+    for jid, last, n, cap in specs:
+        k = 20 if cap is None else cap
+        assert got[jid] == " ".join(f"w{(last + 1 + j) % VOCAB}" for j in range(k)), jid
+    assert got["stop"] == "w101 w102 w103 "
+    assert made["preemptions"] > 0, "the 30-block pool was meant to force preemptions"
+    assert made["blocks"][0] == made["blocks"][1]

@@ -12,7 +12,6 @@ If this number is not far above the GPU's jobs/s the host is the bottleneck.
 """
 import argparse
 import asyncio
-import ctypes as C
 import json
 import os
 import sys
@@ -27,64 +26,6 @@ for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
         break
 os.environ.setdefault("LLMQ_LOG_LEVEL", "WARNING")
 
-import numpy as np  # noqa: E402
-
-from llmq_b200 import lib as L  # noqa: E402
-
-
-class _NoDevice:
-    device = None
-    max_model_len = 512
-
-    def close(self):
-        pass
-
-
-class DryRunEngine:
-    """llmq_b200.model.Engine's call surface over b200q_engine_create_dryrun (no model, no CUDA)"""
-
-    def __init__(self, vocab, max_num_seqs, budget, max_model_len, num_blocks, eos, step_ms=0.0):
-        self.step_s = step_ms / 1e3
-        self.lib = L.load()
-        cfg = L.EngineConfig(max_num_seqs=max_num_seqs, max_num_batched_tokens=budget,
-                             max_model_len=max_model_len, eos_token_id=eos, policy=1)
-        h = C.c_void_p()
-        L.check(self.lib.b200q_engine_create_dryrun(C.byref(cfg), vocab, 16, num_blocks, C.byref(h)))
-        self.handle, self.cap = h, max_num_seqs
-        self._ids = np.zeros(self.cap, np.int64)
-        self._tok = np.zeros(self.cap, np.int32)
-        self._flg = np.zeros(self.cap, np.int32)
-        self.model = _NoDevice()
-        self.model.max_model_len = max_model_len
-        self.steps = 0
-
-    def add_request(self, rid, ids, max_new, ignore_eos=False, temperature=0.0, seed=0):
-        arr = np.ascontiguousarray(ids, dtype=np.int32)
-        rc = self.lib.b200q_engine_add_request(self.handle, int(rid), arr.ctypes.data, arr.size, int(max_new), 1)
-        if rc == -1:
-            raise ValueError(self.lib.b200q_last_error().decode())
-        L.check(rc)
-
-    def abort(self, rid):
-        L.check(self.lib.b200q_engine_abort(self.handle, int(rid)))
-
-    def has_work(self):
-        return bool(self.lib.b200q_engine_has_work(self.handle))
-
-    def step(self):
-        n = C.c_int32(0)
-        L.check(self.lib.b200q_engine_step(self.handle, self._ids.ctypes.data, self._tok.ctypes.data,
-                                           self._flg.ctypes.data, self.cap, C.byref(n)))
-        if self.step_s:
-            time.sleep(self.step_s)  # stands in for the GPU step (GIL released, like the C call)
-        self.steps += 1
-        k = n.value
-        return self._ids[:k], self._tok[:k], self._flg[:k]
-
-    def close(self):
-        if self.handle:
-            self.lib.b200q_engine_destroy(self.handle)
-            self.handle = None
 
 
 def main():
@@ -102,7 +43,7 @@ def main():
 
     import llmq_b200.worker as W
     from llmq_b200 import service as S
-    from llmq_b200.fixtures import build_tokenizer, make_jobs, special_token_ids
+    from llmq_b200.fixtures import DryRunEngine, build_tokenizer, make_jobs, special_token_ids
     from llmq.core.models import Job
 
     tok = build_tokenizer(args.vocab)
@@ -111,7 +52,7 @@ def main():
 
     def dry_build_service(model_name, **kw):
         blocks = args.max_num_seqs * ((args.prompt_tokens + args.out_tokens + 15) // 16 + 1)
-        eng = DryRunEngine(args.vocab, args.max_num_seqs, 4608, 512, blocks, eos, args.step_ms)
+        eng = DryRunEngine(args.vocab, args.max_num_seqs, 4608, 512, blocks, eos, step_ms=args.step_ms)
         made["engine"] = eng
         return S.GenerationService(eng, tok, eos)
 

@@ -67,13 +67,20 @@ def seeded_state_dict(spec: ModelSpec, seed: int = 1234) -> dict:
 
     g = torch.Generator().manual_seed(seed)
     mat = lambda r, c: (torch.randn(r, c, generator=g) * 0.02).to(torch.bfloat16)
-    ones = lambda: torch.ones(spec.hidden, dtype=torch.bfloat16)
+    gemma = spec.arch == "gemma2"
+    if gemma:  # GemmaRMSNorm scales by (1 + w): small random w so that the weights matter
+        ones = lambda: (torch.randn(spec.hidden, generator=g) * 0.1).to(torch.bfloat16)
+        norms = ("input_layernorm", "post_attention_layernorm", "pre_feedforward_layernorm",
+                 "post_feedforward_layernorm")
+    else:
+        ones = lambda: torch.ones(spec.hidden, dtype=torch.bfloat16)
+        norms = ("input_layernorm", "post_attention_layernorm")
     sd = {"model.embed_tokens.weight": mat(spec.vocab, spec.hidden)}
     qd, kd = spec.n_q_heads * spec.head_dim, spec.n_kv_heads * spec.head_dim
     for i in range(spec.n_layers):
         p = f"model.layers.{i}."
-        sd[p + "input_layernorm.weight"] = ones()
-        sd[p + "post_attention_layernorm.weight"] = ones()
+        for n in norms:
+            sd[p + n + ".weight"] = ones()
         sd[p + "self_attn.q_proj.weight"] = mat(qd, spec.hidden)
         sd[p + "self_attn.k_proj.weight"] = mat(kd, spec.hidden)
         sd[p + "self_attn.v_proj.weight"] = mat(kd, spec.hidden)

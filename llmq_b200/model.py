@@ -120,7 +120,7 @@ class ModelSpec:
                 "vocab_size": self.vocab, "rms_norm_eps": self.rms_eps, "rope_theta": self.rope_theta,
                 "tie_word_embeddings": True, "max_position_embeddings": self.max_position_embeddings,
                 "hidden_activation": "gelu_pytorch_tanh", "attention_bias": False,
-                "query_pre_attn_scalar": self.query_pre_attn_scalar or self.head_dim,
+                "query_pre_attn_scalar": int(self.query_pre_attn_scalar or self.head_dim),  # HF: int field
                 "attn_logit_softcapping": self.attn_softcap or None,
                 "final_logit_softcapping": self.final_softcap or None,
                 "sliding_window": self.sliding_window or None, "torch_dtype": "bfloat16",

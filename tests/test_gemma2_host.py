@@ -64,3 +64,40 @@ def test_model_config_struct_carries_arch_fields():
                          attn_scale=0.0625, arch=lib.ARCH_GEMMA2, attn_softcap=50.0, final_softcap=30.0,
                          sliding_window=32, embed_scale=16.0)
     assert h.b200q_model_workspace_bytes(ok) > 0
+
+
+def test_gemma2_model_dir_is_a_real_hf_checkpoint(tmp_path):
+    """write_model_dir(gemma2 spec) -> transformers loads it as Gemma2ForCausalLM; its logits equal
+    the oracle's on the same seeded weights; resolve_model / load_hf_state_dict / fuse_hf_weights
+    (the product's loading path up to the device) see the same tensors."""
+    from transformers import AutoConfig, AutoModelForCausalLM
+
+    from llmq_b200.fixtures import seeded_state_dict, write_model_dir
+    from llmq_b200.model import ModelSpec, fuse_hf_weights, interleave_gate_up, load_hf_state_dict, resolve_model
+    from oracle.gemma2 import Gemma2Dims, Gemma2Oracle
+
+    spec = ModelSpec(hidden=256, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=64, intermediate=512, vocab=1024,
+                     rms_eps=1e-6, rope_theta=10000.0, tie_embeddings=True, max_position_embeddings=256,
+                     name="tiny-gemma2", arch="gemma2", query_pre_attn_scalar=64.0, attn_softcap=50.0,
+                     final_softcap=30.0, sliding_window=16)
+    mdir = write_model_dir(str(tmp_path / "tiny-gemma2"), spec, seed=11)
+    cfg = AutoConfig.from_pretrained(mdir)
+    assert cfg.model_type == "gemma2" and cfg.sliding_window == 16 and cfg.attn_logit_softcapping == 50.0
+    got_spec, got_dir = resolve_model(mdir)
+    assert got_dir == mdir
+    for f in ("arch", "hidden", "n_layers", "n_q_heads", "n_kv_heads", "head_dim", "intermediate", "vocab",
+              "sliding_window", "attn_softcap", "final_softcap", "query_pre_attn_scalar", "tie_embeddings"):
+        assert getattr(got_spec, f) == getattr(spec, f), f
+    sd = seeded_state_dict(spec, 11)
+    fused = dict(fuse_hf_weights(got_spec, load_hf_state_dict(mdir)))
+    assert torch.equal(fused["layers.1.pre_ffn_norm"][0], sd["model.layers.1.pre_feedforward_layernorm.weight"])
+    assert torch.equal(fused["layers.0.gate_up"], interleave_gate_up(sd["model.layers.0.mlp.gate_proj.weight"],
+                                                                      sd["model.layers.0.mlp.up_proj.weight"]))
+    hf = AutoModelForCausalLM.from_pretrained(mdir, torch_dtype=torch.float32, attn_implementation="eager").eval()
+    ids = torch.randint(3, 1000, (1, 40), generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref = hf(ids).logits[0]
+    d = Gemma2Dims(hidden=256, n_layers=2, n_q_heads=4, n_kv_heads=2, head_dim=64, intermediate=512, vocab=1024,
+                   query_pre_attn_scalar=64.0, sliding_window=16, max_pos=256)
+    mine, _ = Gemma2Oracle(d, sd, "fp32").forward(ids[0], torch.arange(40))
+    assert (mine - ref).abs().max().item() < 5e-5

@@ -269,7 +269,6 @@ def workload_config(args, per_gpu_jobs):
 # native arm
 # ------------------------------------------------------------------------------------------------
 def run_native(args):
-    import numpy as np
     import torch
 
     from llmq_b200 import lib as L

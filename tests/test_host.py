@@ -305,3 +305,43 @@ def test_service_over_the_real_cpp_scheduler_dryrun(monkeypatch):
     assert got["stop"] == "w101 w102 w103 "
     assert made["preemptions"] > 0, "the 30-block pool was meant to force preemptions"
     assert made["blocks"][0] == made["blocks"][1]
+
+
+def test_token_table_matches_a_dict_of_lists_model():
+    """the vectorised per-step token store of GenerationService against the obvious model, under
+    random interleavings of allocate / step-append / release, growing rows and widths"""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, 2), st.integers(1, 40), st.integers(0, 10 ** 6)), min_size=1, max_size=120))
+    def run(ops):
+        t = S._TokenTable()
+        model = {}   # slot -> [tokens]
+        caps = {}
+        rng = np.random.default_rng(0)
+        for kind, a, b in ops:
+            if kind == 0:  # allocate a request with max_new = a
+                slot = t.alloc(a, has_stop=bool(b & 1))
+                assert slot not in model and bool(t.has_stop[slot]) == bool(b & 1)
+                model[slot], caps[slot] = [], a
+            elif kind == 1 and model:  # one engine step over a random subset of live, non-full requests
+                live = [s for s in model if len(model[s]) < caps[s]]
+                if not live:
+                    continue
+                pick = rng.permutation(live)[: max(1, a % (len(live) + 1))]
+                toks = rng.integers(0, 50000, size=len(pick)).astype(np.int32)
+                t.append_step(np.asarray(pick, dtype=np.int64), toks)
+                for s, x in zip(pick.tolist(), toks.tolist()):
+                    model[s].append(x)
+            elif kind == 2 and model:  # finish one
+                s = sorted(model)[b % len(model)]
+                assert t.tokens(s) == model[s]
+                t.release(s)
+                del model[s], caps[s]
+            for s in model:
+                assert int(t.n[s]) == len(model[s])
+        for s in model:
+            assert t.tokens(s) == model[s]
+
+    run()

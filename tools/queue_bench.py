@@ -25,7 +25,6 @@ sys.path[:0] = [SHIMS, REF, ROOT]
 async def run(args, port):
     os.environ["B200Q_SHIM_BROKER"] = f"127.0.0.1:{port}"
     os.environ.setdefault("LLMQ_LOG_LEVEL", "WARNING")
-    import aio_pika
     from llmq.core.broker import BrokerManager
     from llmq.core.models import Job, Result
 

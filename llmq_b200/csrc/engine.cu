@@ -538,7 +538,8 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
         e->graphs.clear();
         e->graph_epoch = tuning_epoch();
       }
-      const uint64_t key = (uint64_t)T | ((uint64_t)bt_stride << 16) | ((uint64_t)(any_sampled ? 1 : 0) << 32);
+      // T in bits 0-31, block-table stride in 32-61, sampled flag in 62: no aliasing for any budget
+      const uint64_t key = (uint64_t)(uint32_t)T | ((uint64_t)bt_stride << 32) | ((uint64_t)(any_sampled ? 1 : 0) << 62);
       auto it = e->graphs.find(key);
       if (it == e->graphs.end()) {
         const int64_t l0 = b200q_launch_count();

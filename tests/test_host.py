@@ -345,3 +345,52 @@ def test_token_table_matches_a_dict_of_lists_model():
             assert t.tokens(s) == model[s]
 
     run()
+
+
+def test_engine_failure_rejects_and_requeues_instead_of_dropping(patched, monkeypatch):
+    """SURVEY §8b error convention: only ValueError drops a job (ack).  A device / engine failure
+    must surface as a non-ValueError from _process_job so that the reference's BaseWorker rejects
+    the message with requeue=True (base.py:237-245) and another worker can pick it up; once the
+    engine thread has died every later submit fails the same way (no silent hang)."""
+    made, tok = patched
+
+    class Boom(RuntimeError):
+        pass
+
+    async def main():
+        w = B200Worker("random:llama-3-8b", "fq", tensor_parallel_size=1)
+        await w._initialize_processor()
+        eng = made["engine"]
+        orig = eng.step
+        calls = {"n": 0}
+
+        def step():
+            calls["n"] += 1
+            if calls["n"] == 3:
+                raise Boom("device fell off the bus")
+            return orig()
+
+        eng.step = step
+        results = await asyncio.gather(*[w._process_job(Job(id=f"f{i}", prompt=f"w{50 + i}")) for i in range(6)],
+                                       return_exceptions=True)
+        assert all(isinstance(r, RuntimeError) and not isinstance(r, ValueError) for r in results), results
+        assert "device fell off the bus" in str(results[0])
+        with pytest.raises(RuntimeError, match="engine thread died"):
+            await w._process_job(Job(id="late", prompt="w9"))
+        # and through the reference's message envelope: rejected with requeue, never acked
+        seen = {}
+
+        class Msg:
+            body = json.dumps({"id": "m1", "prompt": "w9"}).encode()
+
+            async def ack(self):
+                seen["ack"] = True
+
+            async def reject(self, requeue=False):
+                seen["reject"] = requeue
+
+        await w._process_message(Msg())
+        assert seen == {"reject": True}
+        await w._cleanup_processor()
+
+    asyncio.run(main())

@@ -394,3 +394,26 @@ def test_engine_failure_rejects_and_requeues_instead_of_dropping(patched, monkey
         await w._cleanup_processor()
 
     asyncio.run(main())
+
+
+def test_reference_quirks_are_replicated_not_fixed(patched):
+    """behaviours of the reference worker that a drop-in must keep.
+    D4 — a prompt is always passed through str.format (ref:llmq/core/models.py:46), so braces in a
+    later pipeline stage's input (= the previous model's output) raise KeyError / IndexError
+    (=> reject + requeue by the base class) or ValueError (=> dropped); D6 — chat jobs report the
+    literal "Chat with N messages" as their prompt."""
+    made, tok = patched
+
+    async def main():
+        w = B200Worker("random:llama-3-8b", "qq", tensor_parallel_size=1)
+        await w._initialize_processor()
+        with pytest.raises(KeyError):
+            await w._process_job(Job(id="b1", prompt="w5 {not_a_field} w6"))
+        with pytest.raises(IndexError):
+            await w._process_job(Job(id="b2", prompt="w5 {} w6"))
+        with pytest.raises(ValueError):
+            await w._process_job(Job(id="b3", prompt="w5 { w6"))
+        assert await w._process_job(Job(id="b4", prompt="w5 {{w6}} {x}", x="w7", temperature=0)) != ""  # escaped braces are fine
+        await w._cleanup_processor()
+
+    asyncio.run(main())

@@ -82,6 +82,9 @@ struct b200q_engine {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   int graph_epoch = 0;  // tuning_epoch() the cached graphs were captured under
   bool admitting = false;  // admission hysteresis state (policy 1)
+  // growth-aware admission (policy 1): running mean of the generated length of finished requests;
+  // < 0 until the first request has finished (then every request is assumed to run to max_new)
+  double est_gen = -1.0;
   // scheduler self-test mode (b200q_engine_create_dryrun): no model, no CUDA — step() builds the
   // batch metadata exactly as in production, checks its invariants and fabricates the "sampled"
   // token as (previous token + 1) mod vocab.  Host-logic tests only; never reachable from the worker.
@@ -92,6 +95,16 @@ struct b200q_engine {
 static void free_request_blocks(b200q_engine* e, Request* r) {
   for (int32_t b : r->blocks) e->free_blocks.push_back(b);
   r->blocks.clear();
+}
+
+// KV blocks request r is still expected to claim beyond `held` blocks: it is assumed to generate
+// min(max_new, max(est_gen, n_generated + 1)) tokens (est_gen < 0: no history yet => max_new)
+static int expected_growth_blocks(const b200q_engine* e, const Request* r, int held) {
+  int gen = r->max_new;
+  if (e->est_gen >= 0.0) gen = std::min(gen, std::max((int)(e->est_gen + 0.999), r->n_generated + 1));
+  const int final_len = std::min(r->n_prompt + gen, e->cfg.max_model_len);
+  const int blocks = (final_len + e->block_size - 1) / e->block_size;
+  return std::max(0, blocks - held);
 }
 
 static bool ensure_blocks(b200q_engine* e, Request* r, int n_tokens_total) {
@@ -343,6 +356,14 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     }
   };
   auto admit_waiting = [&]() {
+    // policy 1 also reserves the blocks the RUNNING requests are expected to grow into (their
+    // expected final length, see expected_growth_blocks): admitting on today's free blocks alone
+    // over-commits the pool under a steady backlog, and every later preemption recomputes a whole
+    // sequence (3 % of all tokens at 4608 x 128-in/128-out on one B200, tools/sched_sim.py).
+    // Requests that outgrow the estimate are still handled by preempt-by-recompute.
+    int64_t growth = 0;
+    if (e->cfg.policy == 1)
+      for (const Request* q : e->running) growth += expected_growth_blocks(e, q, (int)q->blocks.size());
     while (budget > 0 && !e->waiting.empty() && (int)e->running.size() < e->cfg.max_num_seqs) {
       Request* r = e->waiting.front();
       const int n_new = std::min((int)r->tokens.size() - r->n_computed, budget);
@@ -352,10 +373,16 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
       // lets a request start a prefill it cannot finish: it preempts itself at the last block, is
       // re-admitted at once (prefill first) and starves the decodes whose completion would have
       // freed the memory — a livelock found by tests/test_scheduler_dryrun.py.
-      const int need = ((int)r->tokens.size() + e->block_size - 1) / e->block_size - (int)r->blocks.size();
+      const int seq_blocks = ((int)r->tokens.size() + e->block_size - 1) / e->block_size;
+      const int need = seq_blocks - (int)r->blocks.size();
       const int reserve = e->running.empty() ? 0 : (int)e->running.size() / 8 + 1;
       if ((int)e->free_blocks.size() - need < reserve) break;
+      const int r_growth = e->cfg.policy == 1 ? expected_growth_blocks(e, r, seq_blocks) : 0;
+      if (e->cfg.policy == 1 && !e->running.empty() &&
+          (int64_t)e->free_blocks.size() - need - r_growth < growth)
+        break;
       if (!ensure_blocks(e, r, r->n_computed + n_new)) break;
+      growth += r_growth;
       e->waiting.pop_front();
       e->running.push_back(r);
       r->n_sched = n_new;
@@ -621,6 +648,10 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     out_flags[n_ev] = flags;
     ++n_ev;
     if (flags) {
+      // generated-length history for growth-aware admission: mean of the first finishers, then
+      // an exponential average (window ~64 requests)
+      e->est_gen = e->est_gen < 0.0 ? (double)r->n_generated
+                                    : e->est_gen + ((double)r->n_generated - e->est_gen) / 64.0;
       free_request_blocks(e, r);
       e->running.erase(std::find(e->running.begin(), e->running.end(), r));
       e->by_id.erase(r->id);

@@ -361,8 +361,14 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     // over-commits the pool under a steady backlog, and every later preemption recomputes a whole
     // sequence (3 % of all tokens at 4608 x 128-in/128-out on one B200, tools/sched_sim.py).
     // Requests that outgrow the estimate are still handled by preempt-by-recompute.
+    // The reservation only pays while there is a backlog to fill the batch from later: when every
+    // waiting request fits the free slots (the queue is draining) a deferred request would run on
+    // as a small-batch tail of its own, whereas admitting it optimistically costs at most a late
+    // preemption + one recompute step (dry-run: 272 vs 382 steps for 4608 jobs in a pool 1 % short).
+    const bool gate = e->cfg.policy == 1 &&
+                      (int)e->waiting.size() > e->cfg.max_num_seqs - (int)e->running.size();
     int64_t growth = 0;
-    if (e->cfg.policy == 1)
+    if (gate)
       for (const Request* q : e->running) growth += expected_growth_blocks(e, q, (int)q->blocks.size());
     while (budget > 0 && !e->waiting.empty() && (int)e->running.size() < e->cfg.max_num_seqs) {
       Request* r = e->waiting.front();
@@ -377,9 +383,8 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
       const int need = seq_blocks - (int)r->blocks.size();
       const int reserve = e->running.empty() ? 0 : (int)e->running.size() / 8 + 1;
       if ((int)e->free_blocks.size() - need < reserve) break;
-      const int r_growth = e->cfg.policy == 1 ? expected_growth_blocks(e, r, seq_blocks) : 0;
-      if (e->cfg.policy == 1 && !e->running.empty() &&
-          (int64_t)e->free_blocks.size() - need - r_growth < growth)
+      const int r_growth = gate ? expected_growth_blocks(e, r, seq_blocks) : 0;
+      if (gate && !e->running.empty() && (int64_t)e->free_blocks.size() - need - r_growth < growth)
         break;
       if (!ensure_blocks(e, r, r->n_computed + n_new)) break;
       growth += r_growth;

@@ -82,6 +82,7 @@ struct b200q_engine {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   int graph_epoch = 0;  // tuning_epoch() the cached graphs were captured under
   bool admitting = false;  // admission hysteresis state (policy 1)
+  int admit_batch = 0;     // free slots that (re)open admission; 0 = max_num_seqs / 16 (B200Q_ADMIT_BATCH)
   // growth-aware admission (policy 1): running mean of the generated length of finished requests;
   // < 0 until the first request has finished (then every request is assumed to run to max_new)
   double est_gen = -1.0;
@@ -137,6 +138,7 @@ int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b20
   b200q_engine* e = new b200q_engine();
   e->model = model;
   e->cfg = *cfg;
+  if (const char* v = getenv("B200Q_ADMIT_BATCH")) e->admit_batch = atoi(v);
   e->mcfg = mc;
   e->block_size = mc.block_size;
   e->max_blocks_per_seq = (cfg->max_model_len + mc.block_size - 1) / mc.block_size;
@@ -179,6 +181,7 @@ int b200q_engine_create_dryrun(const b200q_engine_config* cfg, int32_t vocab, in
   e->use_graphs = false;
   e->model = nullptr;
   e->cfg = *cfg;
+  if (const char* v = getenv("B200Q_ADMIT_BATCH")) e->admit_batch = atoi(v);
   memset(&e->mcfg, 0, sizeof(e->mcfg));
   e->mcfg.vocab = vocab;
   e->mcfg.block_size = block_size;
@@ -405,7 +408,7 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     // decode-only => no CUDA-graph replay, prefill GEMMs at M ~ 128).  Wait until a batch of
     // slots (1/16 of max_num_seqs) is free, then admit until the slots or the budget run out.
     const int free_slots = e->cfg.max_num_seqs - (int)e->running.size();
-    const int thresh = std::max(1, e->cfg.max_num_seqs / 16);
+    const int thresh = e->admit_batch > 0 ? e->admit_batch : std::max(1, e->cfg.max_num_seqs / 16);
     const bool mid_prefill = !sched.empty();  // an unfinished prompt is in flight: keep the phase going
     if (e->running.empty() || mid_prefill || free_slots >= thresh || e->admitting) {
       const size_t before = e->running.size();

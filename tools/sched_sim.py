@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--gemm-eff", type=float, default=0.88, help="fraction of the sustained bf16 peak (bench.py)")
     ap.add_argument("--attn-eff", type=float, default=0.85, help="fraction of the HBM copy bandwidth (bench.py)")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--quantise", action="store_true", help="price GEMMs by rows padded to the 128-row tile")
     args = ap.parse_args()
 
     from llmq_b200.fixtures import DryRunEngine
@@ -84,7 +85,9 @@ def main():
             if f:
                 ctx.pop(rid, None)
         attn_bytes = dec_ctx * kv_tok + d_pre * 1024 * kv_tok / 16.0 * 0.5  # prefill: ~mean ctx 1024, 16 rows share a read
-        g = max(T * flops_per_token / (peaks["bf16_tflops"] * 1e12 * args.gemm_eff), w_bytes / (peaks["hbm_gbs"] * 1e9))
+        # the persistent GEMMs work in 128-row tiles: a step costs what its padded row count costs
+        Tq = -(-T // 128) * 128 if args.quantise else T
+        g = max(Tq * flops_per_token / (peaks["bf16_tflops"] * 1e12 * args.gemm_eff), w_bytes / (peaks["hbm_gbs"] * 1e9))
         a = attn_bytes / (peaks["hbm_gbs"] * 1e9 * args.attn_eff)
         t_gemm += g
         t_attn += a

@@ -8,13 +8,19 @@ Workload (BASELINE.json `metric`): Llama-3-8B, random-init bf16, 128 prompt toke
 generated tokens out, queue-sharded data parallel — one worker process per GPU, job i of the
 canonical seeded job stream goes to rank i % N, no data-path collective.
 
-A *step* is one batch of `--jobs` jobs per GPU pushed through the continuous-batching engine to
-completion (prefill + 128 greedy decode tokens each).
-  value : output tokens/s with the prompts already tokenised and queued inside the engine
-          (weights, KV pool, workspace resident in HBM) — device-side, max over ranks.
-  e2e   : the same metric through the worker-facing call (`GenerationService.submit`, what
-          `B200Worker._process_job` awaits): host text prompts -> tokenise -> engine thread ->
-          per-step H2D metadata / D2H sampled ids -> detokenise -> host text.
+The engine runs in steady state: `--max-num-seqs` (4608) sequences in flight and a backlog behind
+them that never empties — the situation of a worker on a 100k-prompt queue.  A *step* is `--jobs`
+(1152) COMPLETED jobs per GPU: the timed region is exactly K steps = K x 1152 completions per GPU
+(about 4 s each on one B200), after W untimed steps that include the ramp (the cohort that fills
+the empty engine has staggered output caps, so the batch holds requests of every age).
+  value : output tokens/s (tokens sampled inside the timed region) with the prompts already
+          tokenised and queued inside the engine (weights, KV pool, workspace resident in HBM) —
+          device-side (CUDA events on the engine's stream), max over ranks.
+  e2e   : the same metric through the worker-facing call, `B200Worker._process_job(Job)` — what
+          the reference's `BaseWorker._process_message` awaits — behind an un-acked window of
+          max_num_seqs + jobs messages (the role of VLLM_QUEUE_PREFETCH): host text prompts ->
+          tokenise -> engine thread -> per-step H2D metadata / D2H sampled ids -> detokenise ->
+          host text; min(K, 8) steps by wall clock, max over ranks.
   roofline : live CUDA-event timing of every kernel launch in the timed region (events recorded
           on the engine's stream by libb200q), GEMM = dominant kernel (tensor-bound), plus the
           decode-attention HBM fraction.
@@ -73,23 +79,25 @@ def usable_host_cores() -> int:
     return max(1, min(n, int(os.environ.get("B200Q_CPU_THREADS", "64"))))
 
 
-def ncu_traffic(kernel_substr):
-    """dram read+write bytes per launch of the named kernel from the committed `ncu --set full`
-    capture (profiles/r1_ncu_full_targets.csv: the bench's GEMM shapes at M=4608), or None"""
+def ncu_traffic():
+    """dram read+write bytes per launch of the dominant kernel — the fused gate_up GEMM at the
+    bench shape (M=4608, N=28672, K=4096), `gemm2_bf16_kernel<256,1>` as dispatched there — from
+    the newest committed `ncu --set full` capture under profiles/, or None"""
     import csv
 
-    p = os.path.join(ROOT, "profiles", "r1_ncu_full_targets.csv")
-    try:
-        rows = list(csv.reader(open(p)))
-        hdr, units = rows[0], rows[1]
-        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
-        mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-        for r in rows[2:]:
-            if kernel_substr in r[ik]:
-                return (float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]],
-                        f"ncu --set full, {kernel_substr} (fused gate_up GEMM, M=4608): algorithmic 405 MB")
-    except Exception:
-        pass
+    for fname, kernel in (("r2_ncu_full_targets.csv", "gemm2_bf16_kernel<256, 1>"),
+                          ("r1_ncu_full_targets.csv", "gemm_bf16_kernel<256, 1>")):
+        try:
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", fname))))
+            hdr, units = rows[0], rows[1]
+            ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+            mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            for r in rows[2:]:
+                if kernel in r[ik]:
+                    return (float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]],
+                            f"ncu --set full (profiles/{fname}), {kernel} = fused gate_up GEMM at M=4608: algorithmic 405 MB")
+        except Exception:
+            continue
     return None, "no ncu capture found"
 
 
@@ -232,7 +240,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample, cores = cpu_reference_sample(args.model, args.prompt_tokens, args.out_tokens, args.cpu_budget_s)
+    # each step is a bounded sample (a real prefill + as many decode steps as fit); the per-step
+    # budget shrinks with --steps so that the whole run stays around two minutes of host time
+    budget = max(2.0, min(args.cpu_budget_s, 100.0 / (args.steps + 1)))
+    sample, cores = cpu_reference_sample(args.model, args.prompt_tokens, args.out_tokens, budget)
     if args.warmup > 0:
         sample()  # one warm-up pass faults in the weights; more would only burn host time
     t0 = time.perf_counter()
@@ -245,7 +256,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (cpu)", "data": "synthetic",
-            "config": workload_config(args, per_gpu_jobs=1),
+            "config": workload_config(args),
             "jobs_per_sec": statistics.median(r["jobs_per_s"] for r in res),
             "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -257,87 +268,191 @@ def builtin_weight_gb(model_key: str) -> float:
     return BUILTIN_SPECS[model_key].weight_bytes_per_step() / 1e9
 
 
-def workload_config(args, per_gpu_jobs):
-    return {"workload": f"{args.model} random-init bf16, {args.prompt_tokens}-in/{args.out_tokens}-out greedy, "
-                        f"{per_gpu_jobs} jobs per step per GPU, queue-sharded (job i -> rank i % N)",
+def workload_config(args):
+    """the same dict on both arms (the reference arm runs a bounded sample of this workload)"""
+    return {"workload": f"{args.model} random-init bf16, {args.prompt_tokens}-in/{args.out_tokens}-out greedy, continuous backlog "
+                        f"(queue never empty), {args.max_num_seqs} concurrent sequences per GPU, step = {args.jobs} completed jobs "
+                        "per GPU, queue-sharded (job i -> rank i % N)",
+            "jobs_per_step_per_gpu": args.jobs,
             "max_num_seqs": args.max_num_seqs, "max_num_batched_tokens": args.max_num_batched_tokens,
-            "gpu_memory_utilization": args.gpu_memory_utilization, "kv_block_size": 16, "l2": f"working set per step (weights {builtin_weight_gb(args.model):.0f} GB + KV) >> 126 MB L2, no flush needed",
+            "gpu_memory_utilization": args.gpu_memory_utilization, "kv_block_size": 16, "l2": f"working set per engine step (weights {builtin_weight_gb(args.model):.0f} GB + KV) >> 126 MB L2, no flush needed",
             "parallelism": f"dp{args.gpus} (independent replicas, no collective)"}
 
 
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
+class CudaTimer:
+    """CUDA events on the engine's own stream (torch.cuda.Event only sees torch's current stream)"""
+
+    def __init__(self, torch, stream_ptr):
+        self.stream = torch.cuda.ExternalStream(stream_ptr)
+        self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def start(self):
+        self.e0.record(self.stream)
+
+    def stop(self):
+        self.e1.record(self.stream)
+        self.e1.synchronize()
+
+    def seconds(self):
+        return self.e0.elapsed_time(self.e1) / 1e3
+
+
+class HostTimer:
+    def start(self):
+        self.t0 = time.perf_counter()
+
+    def stop(self):
+        self.t1 = time.perf_counter()
+
+    def seconds(self):
+        return self.t1 - self.t0
+
+
+def dry_run_service(args):
+    """--dry-run: the real C++ scheduler / block manager without a model (tokens are fabricated) so
+    that this script's own host logic (ramp, step accounting, windows, reductions) is testable on a
+    machine without a GPU.  Its JSON line is marked and is never a measurement."""
+    from llmq_b200.fixtures import DryRunEngine, build_tokenizer
+    from llmq_b200.model import BUILTIN_SPECS
+    from llmq_b200.service import GenerationService
+
+    spec = BUILTIN_SPECS[args.model]
+    eng = DryRunEngine(spec.vocab, max_num_seqs=args.max_num_seqs, max_num_batched_tokens=args.max_num_batched_tokens,
+                       max_model_len=args.max_model_len, num_blocks=args.num_blocks or 4 * args.max_num_seqs * (args.max_model_len // 16),
+                       eos_token_id=None)
+    eng.model.spec = spec
+    eng.model.set_profiling = lambda on: None
+    eng.model.collect_profile = lambda reset=False: {n: {"ms": 0.0, "work": 0.0, "launches": 0} for n in
+                                                     ("gemm", "decode_attn", "prefill_attn", "elementwise")}
+    eng.stream_ptr = 0
+    return GenerationService(eng, build_tokenizer(spec.vocab), None)
+
+
+def staggered_caps(n: int, out_tokens: int):
+    """generated-length caps of the first (ramp) cohort: uniform over 1..out_tokens, so that the
+    sequences that fill the empty engine do not all finish on the same step — from then on the
+    batch holds requests of every age, as under a long-running queue"""
+    return [1 + (i * 7919) % out_tokens for i in range(n)]
+
+
 def run_native(args):
+    import numpy as np
     import torch
 
     from llmq_b200 import lib as L
     from llmq_b200.fixtures import make_jobs
+    from llmq_b200.model import Engine
     from llmq_b200.service import GenerationService, build_service
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
-    torch.cuda.set_device(local)
-    L.require_device()
+    dry = args.dry_run  # host-logic self-test of this script (tests/test_bench_host.py): no GPU, no model
     dist = None
+    if not dry:
+        torch.cuda.set_device(local)
+        L.require_device()
     if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL's version banner goes there)
     if world > 1:
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if dry:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    red_dev = "cpu" if dry else "cuda"
 
     def barrier():
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
+        if not dry:
+            torch.cuda.synchronize()
+
+    def reduce(x, op):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=red_dev)
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t.item())
 
     peaks = load_peaks()
-    svc: GenerationService = build_service(
-        f"random:{args.model}", max_num_seqs=args.max_num_seqs, max_model_len=args.max_model_len,
-        gpu_memory_utilization=args.gpu_memory_utilization, max_num_batched_tokens=args.max_num_batched_tokens, seed=1234 + rank,
-        num_blocks=args.num_blocks)
+    if dry:
+        svc = dry_run_service(args)
+    else:
+        svc = build_service(
+            f"random:{args.model}", max_num_seqs=args.max_num_seqs, max_model_len=args.max_model_len,
+            gpu_memory_utilization=args.gpu_memory_utilization, max_num_batched_tokens=args.max_num_batched_tokens,
+            seed=1234 + rank, num_blocks=args.num_blocks)
     if args.gemm_mode:
         L.gemm_set_mode(args.gemm_mode)
-    eng, model, tok = svc.engine, svc.engine.model, svc.tokenizer
+    model, tok = svc.engine.model, svc.tokenizer
     spec = model.spec
-    n_steps_total = args.warmup + args.steps
-    J = args.jobs
-    # canonical seeded job stream; this rank's shard (queue-sharding by job index)
-    total_jobs = 2 * n_steps_total * J * world
-    jobs = make_jobs(total_jobs, spec.vocab, args.prompt_tokens - 1, start=rank, stride=world)
-    jobs_a, jobs_b = jobs[: n_steps_total * J], jobs[n_steps_total * J:]
-    ext_stream = torch.cuda.ExternalStream(eng.stream_ptr)
+    S, J, W, K = args.max_num_seqs, args.jobs, args.warmup, args.steps
+    K_e = min(K, args.e2e_steps)
+    W_e = min(W, 2)
+    # canonical seeded job stream, this rank's shard (queue-sharding by job index).  Each arm needs:
+    # the ramp cohort that fills the empty engine + its timed steps + a backlog that keeps the queue
+    # non-empty until the clock stops (the worker is never starved: a 100k-prompt queue behind it)
+    n_a = S + (W + K) * J + S + J
+    n_b = S + (W_e + K_e) * J + S + J
+    jobs = make_jobs((n_a + n_b) * world, spec.vocab, args.prompt_tokens - 1, start=rank, stride=world)
+    jobs_a, jobs_b = jobs[:n_a], jobs[n_a:]
+    caps = staggered_caps(S, args.out_tokens)
 
-    # ---- arm A: engine-direct (prompts tokenised and queued before the clock starts) ----
+    # ---- arm A: engine-direct (prompts tokenised and queued inside the engine before the clock) ----
+    eng = svc.engine
+    timer = HostTimer() if dry else CudaTimer(torch, eng.stream_ptr)
+    enc = svc.encode
+    for i, j in enumerate(jobs_a):
+        eng.add_request(i, enc(j["prompt"]), caps[i] if i < S else args.out_tokens, ignore_eos=True)
     PROFILE_EVERY = 8
-    profile_on = [False]
+    state = {"finished": 0, "tokens": 0, "k": 0, "profile": False}
 
-    def step_direct(batch_jobs):
-        ids = [tok(j["prompt"], add_special_tokens=True).input_ids for j in batch_jobs]
-        for i, p in enumerate(ids):
-            eng.add_request(i, p, args.out_tokens, ignore_eos=True)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(ext_stream)
-        n_tok, k = 0, 0
-        while eng.has_work():
-            # per-launch CUDA-event profiling on every PROFILE_EVERY-th engine step only: the sampled
-            # steps give the live roofline numbers, the others run exactly as in production
-            # (CUDA-graph replay of decode steps included), so `value` is not perturbed
-            if profile_on[0]:
-                model.set_profiling(k % PROFILE_EVERY == 0)
-            _, toks, _ = eng.step()
-            n_tok += len(toks)
-            k += 1
-        e1.record(ext_stream)
-        barrier()
-        return e0.elapsed_time(e1) / 1e3, n_tok
+    def run_until(n_finished):
+        # per-launch CUDA-event profiling on every PROFILE_EVERY-th engine step only: the sampled
+        # steps give the live roofline numbers, the others run exactly as in production
+        # (CUDA-graph replay of decode steps included), so `value` is not perturbed
+        while state["finished"] < n_finished:
+            if state["profile"]:
+                model.set_profiling(state["k"] % PROFILE_EVERY == 0)
+            _, toks, flags = eng.step()
+            state["tokens"] += len(toks)
+            state["finished"] += int(np.count_nonzero(flags))
+            state["k"] += 1
 
-    # ---- arm B: end to end through the worker-facing service call (host text in / text out) ----
+    run_until(W * J)                          # W untimed warm-up steps (the ramp is part of them)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    state["profile"] = True
+    model.collect_profile(reset=True)
+    st0, launches0, tok0, fin0 = eng.stats(), L.launch_count(), state["tokens"], state["finished"]
+    barrier()
+    timer.start()
+    run_until(fin0 + K * J)                   # EXACTLY K steps of J completed jobs each
+    timer.stop()
+    barrier()
+    t_a = reduce(timer.seconds(), "MAX")
+    model.set_profiling(False)
+    prof = model.collect_profile(reset=True)
+    state["profile"] = False
+    launches = L.launch_count() - launches0
+    st1 = eng.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    toks_a = state["tokens"] - tok0
+    jobs_a_done = state["finished"] - fin0
+    value = reduce(toks_a, "SUM") / t_a
+    jobs_per_s = reduce(jobs_a_done, "SUM") / t_a
+    waiting_left = st1.waiting
+    eng.close()                               # drops the backlog that kept the queue non-empty
+
+    # ---- arm B: end to end through the worker-facing call (host text in / text out) ----
     os.environ["VLLM_MAX_TOKENS"] = str(args.out_tokens)
     os.environ["B200Q_TEMPERATURE"] = "0"  # the workload is greedy (oracle mode); the worker's default is 0.7
     os.environ.setdefault("LLMQ_LOG_LEVEL", "WARNING")
@@ -346,83 +461,63 @@ def run_native(args):
 
     from llmq_b200.worker import B200Worker
 
+    if dry:
+        svc.engine = eng = dry_run_service(args).engine
+    else:
+        svc.engine = eng = Engine(model, max_num_seqs=S, max_num_batched_tokens=args.max_num_batched_tokens,
+                                  max_model_len=args.max_model_len, eos_token_id=svc.eos_token_id)
     worker = B200Worker(f"random:{args.model}", "bench-queue", tensor_parallel_size=1)
     worker.service = svc  # the engine built above (one model per process)
+    for i in range(min(S, len(jobs_b))):
+        jobs_b[i]["max_tokens"] = caps[i]     # ramp cohort: staggered caps through the per-job extra
+    window = S + J                            # un-acked window, the role of VLLM_QUEUE_PREFETCH
 
-    async def _e2e(batch_jobs):
-        # the reference-facing call: BaseWorker._process_message awaits exactly this coroutine
+    async def e2e_stream():
+        # what BaseWorker does with a prefetch window: every delivered message is its own task
+        # awaiting B200Worker._process_job(Job); a finished one lets the broker deliver the next
+        loop = asyncio.get_running_loop()
+        sem = asyncio.Semaphore(window)
+        res = {"done": 0, "tok": 0, "t0": None, "t1": None, "tok0": 0, "sb0": None, "sb1": None}
+        stop = asyncio.Event()
+        if W_e == 0:
+            res["t0"], res["sb0"] = time.perf_counter(), eng.stats()
+
         async def one(j):
-            text = await worker._process_job(Job(**j))
-            return len(text.split())
+            try:
+                text = await worker._process_job(Job(**j))
+            finally:
+                sem.release()
+            res["done"] += 1
+            res["tok"] += len(text.split())   # one word per ordinary token of the synthetic vocab
+            if res["done"] == W_e * J:
+                res["t0"], res["tok0"], res["sb0"] = time.perf_counter(), res["tok"], eng.stats()
+            elif res["done"] == (W_e + K_e) * J:
+                res["t1"], res["sb1"] = time.perf_counter(), eng.stats()
+                res["tok1"] = res["tok"]
+                stop.set()
 
-        return await asyncio.gather(*[one(j) for j in batch_jobs])
+        tasks = []
+        for j in jobs_b:
+            await sem.acquire()
+            if stop.is_set():
+                break
+            tasks.append(loop.create_task(one(j)))
+        await stop.wait()
+        for t in tasks:
+            t.cancel()
+        await asyncio.gather(*tasks, return_exceptions=True)
+        return res
 
-    def step_e2e(batch_jobs):
-        barrier()
-        t0 = time.perf_counter()
-        res = asyncio.run(_e2e(batch_jobs))
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        barrier()
-        return dt, sum(res)  # generated tokens: one word per ordinary token of the synthetic vocab
-
-    def reduce_max(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def reduce_sum(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    # ---------------- arm A ----------------
-    for s in range(args.warmup):
-        step_direct(jobs_a[s * J:(s + 1) * J])
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    profile_on[0] = True
-    model.collect_profile(reset=True)
-    st0 = eng.stats()
-    launches0 = L.launch_count()
-    times_a, toks_a = [], 0
-    barrier()
-    for s in range(args.warmup, n_steps_total):
-        dt, n = step_direct(jobs_a[s * J:(s + 1) * J])
-        times_a.append(reduce_max(dt))
-        toks_a += n
-    barrier()
-    prof = model.collect_profile(reset=True)
-    profile_on[0] = False
-    model.set_profiling(False)
-    launches = L.launch_count() - launches0
-    st1 = eng.stats()
-    clocks = sampler.stop() if rank == 0 else None
-    total_a = sum(times_a)
-    toks_all = reduce_sum(toks_a)
-    value = toks_all / total_a
-    jobs_per_s = world * J * args.steps / total_a
-
-    # ---------------- arm B (e2e) ----------------
-    # the GPU side is already warm (W warm-up + K timed steps of the same kernels and shapes above);
-    # one more untimed step warms the host side of this arm (tokenizer, asyncio, engine thread)
     svc.start()
-    w_b = min(1, args.warmup)
-    step_e2e(jobs_b[:J]) if w_b else None
-    sb0 = eng.stats()
-    times_b, toks_b = [], 0
-    for s in range(w_b, w_b + args.steps):
-        dt, n = step_e2e(jobs_b[s * J:(s + 1) * J])
-        times_b.append(reduce_max(dt))
-        toks_b += n
-    sb1 = eng.stats()
+    barrier()
+    res = asyncio.run(e2e_stream())
     svc.stop()
-    e2e_value = reduce_sum(toks_b) / sum(times_b)
+    if not dry:
+        torch.cuda.synchronize()
+    t_b = reduce(res["t1"] - res["t0"], "MAX")
+    e2e_value = reduce(res["tok1"] - res["tok0"], "SUM") / t_b
+    e2e_jobs = world * K_e * J / t_b
+    sb0, sb1 = res["sb0"], res["sb1"]
 
     # ---------------- rooflines ----------------
     g = prof["gemm"]
@@ -431,17 +526,17 @@ def run_native(args):
     dec_gbs = d["work"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
     dev_ms = sum(v["ms"] for v in prof.values())
     shares = {k: round(v["ms"] / dev_ms, 4) if dev_ms else 0 for k, v in prof.items()}
-    roofline = {"bound": "tensor", "kernel": "b200q::gemm_bf16_kernel<BN> (tcgen05)", "achieved": round(gemm_tflops, 1),
+    roofline = {"bound": "tensor", "kernel": "b200q::gemm2_bf16_kernel<256,*> (tcgen05 cta_group::2, the variant dispatched at M=4608) / gemm_bf16_kernel",
+                "achieved": round(gemm_tflops, 1),
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": round(gemm_tflops / peaks["bf16_tflops"], 4),
                 "traffic": None, "peak_source": peaks["source"],
                 "launch_avg_ms": round(g["ms"] / max(g["launches"], 1), 5), "launches": g["launches"],
                 "share_of_device_time": shares}
     if args.model == "llama-3-8b":  # the committed ncu capture is of this model's fused gate_up GEMM
-        roofline["traffic"], roofline["traffic_note"] = ncu_traffic("gemm_bf16_kernel<256, 1>")
+        roofline["traffic"], roofline["traffic_note"] = ncu_traffic()
     roofline_dec = {"bound": "hbm", "kernel": f"b200q::decode_attn_stream_kernel<{spec.head_dim},16> (B*n_kv >= 16*SMs) / decode_attn_kernel", "achieved": round(dec_gbs, 1),
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(dec_gbs / peaks["hbm_gbs"], 4),
                     "launch_avg_ms": round(d["ms"] / max(d["launches"], 1), 5), "launches": d["launches"]}
-    # whole-step decode HBM roofline fraction: algorithmic bytes per output token
     steps_a = st1.steps - st0.steps
     dec_tokens = st1.tokens_decoded - st0.tokens_decoded
     if rank == 0:
@@ -454,23 +549,31 @@ def run_native(args):
                    "sample": f"1 job: real {args.prompt_tokens}-token prefill ({r['t_prefill_s']:.2f} s) + {r['decode_steps_timed']} timed decode "
                              f"steps ({r['s_per_decode_token'] * 1e3:.1f} ms/token) extrapolated to {args.out_tokens} out tokens; torch-CPU fp32 "
                              "oracle, all host threads, all decoder layers share one random layer's weights"}
-        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(total_a / args.steps * 1e3, 2), "higher_is_better": True,
+        e2e_eng_steps = max(sb1.steps - sb0.steps, 1)
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": round(t_a / K * 1e3, 2), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(args, J), "jobs_per_sec": round(jobs_per_s, 2),
+                "config": workload_config(args), "jobs_per_sec": round(jobs_per_s, 2),
                 "e2e": {"value": round(e2e_value, 1), "unit": UNIT,
-                        "jobs_per_sec": round(world * J * args.steps / sum(times_b), 2),
-                        "h2d_bytes_per_step": int((sb1.h2d_bytes - sb0.h2d_bytes) / args.steps),
-                        "d2h_bytes_per_step": int((sb1.d2h_bytes - sb0.d2h_bytes) / args.steps),
-                        "note": "B200Worker._process_job(Job) on host text: format prompt -> tokenise -> engine thread (H2D metadata / D2H ids every step) -> detokenised text"},
+                        "jobs_per_sec": round(e2e_jobs, 2), "steps": K_e, "warmup": W_e,
+                        "h2d_bytes_per_step": int((sb1.h2d_bytes - sb0.h2d_bytes) / K_e),
+                        "d2h_bytes_per_step": int((sb1.d2h_bytes - sb0.d2h_bytes) / K_e),
+                        "engine_steps_per_step": round(e2e_eng_steps / K_e, 1),
+                        "note": "B200Worker._process_job(Job) on host text behind an un-acked window of max_num_seqs + J jobs "
+                                "(BaseWorker's prefetch): format prompt -> tokenise -> engine thread (H2D metadata / D2H ids every "
+                                "engine step) -> detokenised text"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "roofline_decode_attn": roofline_dec,
-                "engine": {"engine_steps_per_bench_step": steps_a / args.steps, "decode_tokens": int(dec_tokens),
+                "engine": {"engine_steps_per_bench_step": steps_a / K, "decode_tokens": int(dec_tokens),
+                           "prefill_tokens": int(st1.tokens_prefilled - st0.tokens_prefilled),
                            "preemptions": int(st1.preemptions - st0.preemptions), "kv_blocks": int(st1.total_blocks),
+                           "running_at_end": int(st1.running), "backlog_at_end": int(waiting_left),
                            "device_ms_profiled": round(dev_ms, 1), "profiled_engine_steps": f"1 of every {PROFILE_EVERY}",
-                           "wall_ms_timed": round(total_a * 1e3, 1)},
+                           "wall_ms_timed": round(t_a * 1e3, 1)},
                 "cpu_baseline": cpu}
-        print(json.dumps(line))
+        if dry:
+            line["dry_run"] = "host-logic self-test: C++ scheduler without a model, NOT a measurement"
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -487,7 +590,9 @@ def main():
     ap.add_argument("--model", default="llama-3-8b")
     # 4608 = 36 x 128 rows: with 148 SMs every projection's tile count is within 3 % of a whole
     # number of rounds of the persistent GEMM loop; the KV pool holds them all
-    ap.add_argument("--jobs", type=int, default=4608, help="jobs per step per GPU")
+    ap.add_argument("--jobs", type=int, default=1152,
+                    help="completed jobs per step per GPU (a quarter of the 4608 concurrent sequences)")
+    ap.add_argument("--e2e-steps", type=int, default=8, help="the e2e arm times min(--steps, this) steps")
     ap.add_argument("--num-blocks", type=int, default=None, help="KV pool size in 16-token blocks (default: from gpu_memory_utilization)")
     ap.add_argument("--gemm-mode", type=int, default=0, help="tuning hook: 0 auto, 1 1-CTA kernels, 2 2-CTA kernel")
     ap.add_argument("--prompt-tokens", type=int, default=128)
@@ -497,8 +602,9 @@ def main():
     ap.add_argument("--max-num-batched-tokens", type=int, default=4608,
                     help="36 x 128 like the decode batch: A operand stays L2-resident (measured +1 %% over 9472)")
     ap.add_argument("--max-model-len", type=int, default=512)
-    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dry-run", action="store_true", help="host-logic self-test without a GPU (not a measurement)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -310,6 +310,10 @@ int b200q_engine_add_request(b200q_engine_t e, int64_t req_id, const int32_t* pr
 int b200q_engine_add_request_sampled(b200q_engine_t e, int64_t req_id, const int32_t* prompt_ids,
                                      int32_t n_prompt, int32_t max_new_tokens, int32_t ignore_eos,
                                      float temperature, uint64_t seed);
+/* every id in ids[0..n) ends a request (replaces the single cfg.eos_token_id): vLLM stops on
+ * tokenizer.eos_token_id plus all eos ids of generation_config.json (vllm/sampling_params.py
+ * update_from_generation_config), which the reference worker inherits (vllm_worker.py:161-165). */
+int b200q_engine_set_stop_ids(b200q_engine_t e, const int32_t* ids, int32_t n);
 int b200q_engine_abort(b200q_engine_t e, int64_t req_id);
 /* 1 if any request is waiting or running */
 int b200q_engine_has_work(b200q_engine_t e);

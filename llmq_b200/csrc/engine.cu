@@ -71,6 +71,14 @@ struct b200q_engine {
   int32_t* d_out = nullptr;
 
   b200q_engine_stats stats{};
+  // every token id that ends a request (cfg.eos_token_id plus b200q_engine_set_stop_ids):
+  // Llama-3.x-Instruct lists three ids, gemma-2-it adds <end_of_turn> in generation_config.json
+  std::vector<int32_t> stop_ids;
+  bool is_stop_id(int32_t t) const {
+    for (int32_t s : stop_ids)
+      if (s == t) return true;
+    return false;
+  }
 
   // CUDA graphs of the forward for decode-only steps, keyed by (tokens, block-table stride,
   // sampled?) — every device pointer in the batch is a fixed function of that key.  Removes the
@@ -138,6 +146,7 @@ int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b20
   b200q_engine* e = new b200q_engine();
   e->model = model;
   e->cfg = *cfg;
+  if (cfg->eos_token_id >= 0) e->stop_ids.push_back(cfg->eos_token_id);
   if (const char* v = getenv("B200Q_ADMIT_BATCH")) e->admit_batch = atoi(v);
   e->mcfg = mc;
   e->block_size = mc.block_size;
@@ -181,6 +190,7 @@ int b200q_engine_create_dryrun(const b200q_engine_config* cfg, int32_t vocab, in
   e->use_graphs = false;
   e->model = nullptr;
   e->cfg = *cfg;
+  if (cfg->eos_token_id >= 0) e->stop_ids.push_back(cfg->eos_token_id);
   if (const char* v = getenv("B200Q_ADMIT_BATCH")) e->admit_batch = atoi(v);
   memset(&e->mcfg, 0, sizeof(e->mcfg));
   e->mcfg.vocab = vocab;
@@ -264,6 +274,14 @@ int b200q_engine_add_request_sampled(b200q_engine_t e, int64_t req_id, const int
   Request* r = e->by_id[req_id];
   r->temperature = temperature;
   r->seed = seed;
+  return B200Q_OK;
+}
+
+int b200q_engine_set_stop_ids(b200q_engine_t e, const int32_t* ids, int32_t n) {
+  B200Q_CHECK_ARG(e && (ids || n == 0) && n >= 0 && n <= 64, "set_stop_ids: bad argument (n=%d, at most 64 ids)", n);
+  for (int i = 0; i < n; ++i)
+    B200Q_CHECK_ARG(ids[i] >= 0 && ids[i] < e->mcfg.vocab, "set_stop_ids: id %d out of range", ids[i]);
+  e->stop_ids.assign(ids, ids + n);
   return B200Q_OK;
 }
 
@@ -566,15 +584,19 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     }
     int rc = B200Q_OK;
     bool launched = false;
-    if (e->use_graphs && n_tiles == 0 && T == n_dec && !model_is_profiling(e->model) &&
+    if (e->use_graphs && n_tiles == 0 && T == n_dec && T < (1 << 21) && bt_stride < (1 << 20) &&
+        !model_is_profiling(e->model) &&
         e->stats.steps >= 2 /* first steps run eagerly: one-time attribute/occupancy/scratch setup */) {
       if (e->graph_epoch != tuning_epoch()) {  // a tuning hook changed kernel selection: rebuild
         for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
         e->graphs.clear();
         e->graph_epoch = tuning_epoch();
       }
-      // T in bits 0-31, block-table stride in 32-61, sampled flag in 62: no aliasing for any budget
-      const uint64_t key = (uint64_t)(uint32_t)T | ((uint64_t)bt_stride << 32) | ((uint64_t)(any_sampled ? 1 : 0) << 62);
+      // everything the captured forward bakes in: T (bits 0-20), sampling rows (21-41: a decode-only
+      // step can carry a single-token mid-prefill row that does not sample), block-table stride
+      // (42-61), sampled flag (62).  T < 2^21 is checked by the caller's condition above.
+      const uint64_t key = (uint64_t)(uint32_t)T | ((uint64_t)(uint32_t)n_sample << 21) |
+                           ((uint64_t)bt_stride << 42) | ((uint64_t)(any_sampled ? 1 : 0) << 62);
       auto it = e->graphs.find(key);
       if (it == e->graphs.end()) {
         const int64_t l0 = b200q_launch_count();
@@ -647,7 +669,7 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     r->tokens.push_back(t);
     r->n_generated++;
     int flags = 0;
-    if (!r->ignore_eos && e->cfg.eos_token_id >= 0 && t == e->cfg.eos_token_id)
+    if (!r->ignore_eos && e->is_stop_id(t))
       flags = B200Q_FLAG_FINISHED_EOS;
     else if (r->n_generated >= r->max_new || (int)r->tokens.size() >= e->cfg.max_model_len)
       flags = B200Q_FLAG_FINISHED_LENGTH;

@@ -159,18 +159,23 @@ class DryRunEngine:
     constructs it.  `step_ms` stands in for the device time of a step (sleep, GIL released)."""
 
     def __init__(self, vocab: int, max_num_seqs: int, max_num_batched_tokens: int, max_model_len: int,
-                 num_blocks: int, eos_token_id: Optional[int] = None, policy: int = 1, step_ms: float = 0.0):
+                 num_blocks: int, eos_token_id=None, policy: int = 1, step_ms: float = 0.0):
         import ctypes as C
 
         from . import lib as L
 
         self._C, self._L = C, L
         self.lib = L.load()
+        stop_ids = [] if eos_token_id is None else (
+            [int(eos_token_id)] if isinstance(eos_token_id, int) else sorted({int(x) for x in eos_token_id}))
         cfg = L.EngineConfig(max_num_seqs=max_num_seqs, max_num_batched_tokens=max_num_batched_tokens,
                              max_model_len=max_model_len,
-                             eos_token_id=-1 if eos_token_id is None else int(eos_token_id), policy=policy)
+                             eos_token_id=stop_ids[0] if stop_ids else -1, policy=policy)
         h = C.c_void_p()
         L.check(self.lib.b200q_engine_create_dryrun(C.byref(cfg), vocab, 16, num_blocks, C.byref(h)))
+        if len(stop_ids) > 1:
+            L.check(self.lib.b200q_engine_set_stop_ids(h, (C.c_int32 * len(stop_ids))(*stop_ids), len(stop_ids)))
+        self.max_model_len = max_model_len
         self.handle, self.cap = h, max_num_seqs
         self._ids = np.zeros(self.cap, np.int64)
         self._tok = np.zeros(self.cap, np.int32)

@@ -155,6 +155,7 @@ SIGNATURES = {
     "b200q_engine_destroy": (_i, [_vp]),
     "b200q_engine_add_request": (_i, [_vp, _i64, _vp, C.c_int32, C.c_int32, C.c_int32]),
     "b200q_engine_add_request_sampled": (_i, [_vp, _i64, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64]),
+    "b200q_engine_set_stop_ids": (_i, [_vp, _vp, C.c_int32]),
     "b200q_engine_abort": (_i, [_vp, _i64]),
     "b200q_engine_has_work": (_i, [_vp]),
     "b200q_engine_step": (_i, [_vp, _vp, _vp, _vp, C.c_int32, C.POINTER(C.c_int32)]),

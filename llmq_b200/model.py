@@ -21,6 +21,15 @@ from . import lib as L
 BLOCK_SIZE = 16
 
 
+def _as_id_tuple(v) -> Tuple[int, ...]:
+    """eos_token_id in HF configs is an int, a list of ints, or absent"""
+    if v is None:
+        return ()
+    if isinstance(v, (list, tuple)):
+        return tuple(int(x) for x in v if x is not None)
+    return (int(v),)
+
+
 @dataclass
 class ModelSpec:
     hidden: int
@@ -37,6 +46,9 @@ class ModelSpec:
     max_position_embeddings: int = 8192
     eos_token_id: Optional[int] = None
     bos_token_id: Optional[int] = None
+    # every id that ends generation (config.json lists + generation_config.json); eos_token_id is
+    # the first of them.  vLLM stops on tokenizer.eos_token_id plus all generation_config ids.
+    eos_token_ids: Tuple[int, ...] = ()
     name: str = "llama"
     # architecture: "llama" (Llama / Mistral-style decoders) or "gemma2" 
     arch: str = "llama"
@@ -71,9 +83,8 @@ class ModelSpec:
         scaling = cfg.get("rope_scaling")
         if scaling is None and rp and rp.get("rope_type", "default") not in ("default", None):
             scaling = rp
-        eos = cfg.get("eos_token_id")
-        if isinstance(eos, list):
-            eos = eos[0]
+        eos_all = _as_id_tuple(cfg.get("eos_token_id"))
+        eos = eos_all[0] if eos_all else None
         return ModelSpec(
             hidden=cfg["hidden_size"], n_layers=cfg["num_hidden_layers"],
             n_q_heads=cfg["num_attention_heads"],
@@ -82,7 +93,8 @@ class ModelSpec:
             rms_eps=cfg.get("rms_norm_eps", 1e-5), rope_theta=float(theta), rope_scaling=scaling,
             tie_embeddings=bool(cfg.get("tie_word_embeddings", False)),
             max_position_embeddings=cfg.get("max_position_embeddings", 8192),
-            eos_token_id=eos, bos_token_id=cfg.get("bos_token_id"), name=name,
+            eos_token_id=eos, eos_token_ids=eos_all, bos_token_id=cfg.get("bos_token_id"), name=name,
+            sliding_window=int(cfg.get("sliding_window") or 0) if arch == "MistralForCausalLM" else 0,
         )
 
     @staticmethod
@@ -93,9 +105,8 @@ class ModelSpec:
         if lt and any((t == "sliding_attention") != (i % 2 == 0) for i, t in enumerate(lt)):
             raise ValueError("gemma2: only the stock layer pattern (even layers sliding) is implemented")
         rp = cfg.get("rope_parameters") if isinstance(cfg.get("rope_parameters"), dict) else None
-        eos = cfg.get("eos_token_id")
-        if isinstance(eos, list):
-            eos = eos[0]
+        eos_all = _as_id_tuple(cfg.get("eos_token_id"))
+        eos = eos_all[0] if eos_all else None
         return ModelSpec(
             hidden=cfg["hidden_size"], n_layers=cfg["num_hidden_layers"],
             n_q_heads=cfg["num_attention_heads"], n_kv_heads=cfg["num_key_value_heads"],
@@ -104,7 +115,7 @@ class ModelSpec:
             rope_theta=float(cfg.get("rope_theta") or (rp or {}).get("rope_theta") or 10000.0),
             rope_scaling=None, tie_embeddings=True,
             max_position_embeddings=cfg.get("max_position_embeddings", 8192),
-            eos_token_id=eos, bos_token_id=cfg.get("bos_token_id"), name=name, arch="gemma2",
+            eos_token_id=eos, eos_token_ids=eos_all, bos_token_id=cfg.get("bos_token_id"), name=name, arch="gemma2",
             query_pre_attn_scalar=float(cfg.get("query_pre_attn_scalar", cfg["head_dim"])),
             attn_softcap=float(cfg.get("attn_logit_softcapping") or 0.0),
             final_softcap=float(cfg.get("final_logit_softcapping") or 0.0),
@@ -301,6 +312,10 @@ class NativeModel:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.lib = L.load()
         self.max_model_len = min(max_model_len, spec.max_position_embeddings)
+        if spec.arch != "gemma2" and spec.sliding_window:
+            # Mistral-style window on every layer: not implemented as a window — the context is
+            # capped to it instead, so the window never bites and results stay exact
+            self.max_model_len = min(self.max_model_len, spec.sliding_window)
         self.cfg = L.ModelConfig(
             hidden=spec.hidden, n_layers=spec.n_layers, n_q_heads=spec.n_q_heads,
             n_kv_heads=spec.n_kv_heads, head_dim=spec.head_dim, intermediate=spec.intermediate,
@@ -308,7 +323,8 @@ class NativeModel:
             max_pos=self.max_model_len, tie_embeddings=int(spec.tie_embeddings),
             rms_eps=spec.rms_eps, attn_scale=spec.attn_scale,
             arch=L.ARCH_GEMMA2 if spec.arch == "gemma2" else L.ARCH_LLAMA,
-            sliding_window=spec.sliding_window, attn_softcap=spec.attn_softcap,
+            sliding_window=spec.sliding_window if spec.arch == "gemma2" else 0,
+            attn_softcap=spec.attn_softcap,
             final_softcap=spec.final_softcap, embed_scale=spec.embed_scale)
         h = C.c_void_p()
         L.check(self.lib.b200q_model_create(C.byref(self.cfg), C.byref(h)))
@@ -328,19 +344,32 @@ class NativeModel:
         L.check(self.lib.b200q_model_bind_workspace(h, self.workspace.data_ptr(), ws_bytes))
         block_bytes = spec.n_layers * 2 * spec.n_kv_heads * BLOCK_SIZE * spec.head_dim * 2
         if num_blocks is None:
-            torch.cuda.synchronize(self.device)
-            free, total = torch.cuda.mem_get_info(self.device)
-            # same meaning as vLLM's gpu_memory_utilization: the worker may use this fraction of
-            # the device; what is left after weights + workspace becomes the paged KV pool
-            usable = int(total * gpu_memory_utilization) - (total - free)
-            num_blocks = max(usable // block_bytes, 0)
-        if num_blocks < (self.max_model_len + BLOCK_SIZE - 1) // BLOCK_SIZE:
-            raise MemoryError(f"KV pool of {num_blocks} blocks cannot hold one max_model_len sequence")
+            num_blocks = self.pool_blocks_for(gpu_memory_utilization, block_bytes)
+        if num_blocks < 1:
+            raise MemoryError(
+                f"KV pool of {num_blocks} blocks: gpu_memory_utilization={gpu_memory_utilization} leaves no "
+                "room for a KV cache after weights and workspace")
+        if num_blocks * BLOCK_SIZE < self.max_model_len:
+            # vLLM refuses to start here; the worker serves what the pool can hold instead
+            self.max_model_len = int(num_blocks) * BLOCK_SIZE
         self.num_blocks = int(num_blocks)
         self.kv = torch.zeros(spec.n_layers, self.num_blocks, 2, spec.n_kv_heads, BLOCK_SIZE,
                               spec.head_dim, dtype=torch.bfloat16, device=self.device)
         L.check(self.lib.b200q_model_bind_kv(h, self.kv.data_ptr(), self.num_blocks))
         torch.cuda.synchronize(self.device)
+
+    def pool_blocks_for(self, gpu_memory_utilization: float, block_bytes: int) -> int:
+        """KV blocks that fit `gpu_memory_utilization` of the device — vLLM's meaning of the knob
+        (ref:llmq/workers/vllm_worker.py:107): the worker may use that fraction of the device; what
+        is left after weights + workspace becomes the paged KV pool.  Memory this process has freed
+        back to torch's caching allocator (a previous engine's pool, fp32 temporaries of the weight
+        synthesis) is NOT in use: it is released to the driver first, otherwise cudaMemGetInfo still
+        counts it and a second engine in the same process is sized to nothing."""
+        torch.cuda.synchronize(self.device)
+        torch.cuda.empty_cache()
+        free, total = torch.cuda.mem_get_info(self.device)
+        usable = int(total * gpu_memory_utilization) - (total - free)
+        return max(usable // block_bytes, 0)
 
     def logits_view(self, n: int) -> torch.Tensor:
         """bf16 [n, vocab] view of the logits written by the last forward (tests only)."""
@@ -359,30 +388,44 @@ class NativeModel:
                 for i, n in enumerate(L.PROF_NAMES)}
 
     def close(self):
+        """destroy the native handle and give the device memory back (weights, KV pool, workspace):
+        the next engine built in this process must be able to size its pool from it"""
         if self.handle:
+            torch.cuda.synchronize(self.device)
             self.lib.b200q_model_destroy(self.handle)
             self.handle = None
+            self._keep.clear()
+            self.kv = self.workspace = self.rope = None
+            torch.cuda.empty_cache()
 
 
 class Engine:
     """Python face of b200q_engine: add requests, run steps, get (req_id, token, flags) events."""
 
     def __init__(self, model: NativeModel, *, max_num_seqs: int, max_num_batched_tokens: int,
-                 max_model_len: Optional[int] = None, eos_token_id: Optional[int] = None,
+                 max_model_len: Optional[int] = None, eos_token_id=None,
                  policy: Optional[int] = None):
+        """eos_token_id: None, one id, or an iterable of ids — every one of them ends a request
+        (Llama-3.x-Instruct lists three, gemma-2-it adds <end_of_turn> in generation_config.json)"""
         import numpy as np
 
         self.model = model
         self.lib = model.lib
         self.np = np
+        stop_ids = [] if eos_token_id is None else (
+            [int(eos_token_id)] if isinstance(eos_token_id, int) else sorted({int(x) for x in eos_token_id}))
+        self.max_model_len = min(max_model_len or model.max_model_len, model.max_model_len)
         ecfg = L.EngineConfig(
             max_num_seqs=max_num_seqs, max_num_batched_tokens=max_num_batched_tokens,
-            max_model_len=max_model_len or model.max_model_len,
-            eos_token_id=-1 if eos_token_id is None else int(eos_token_id),
+            max_model_len=self.max_model_len,
+            eos_token_id=stop_ids[0] if stop_ids else -1,
             policy=int(os.environ.get("B200Q_SCHED_POLICY", "1")) if policy is None else int(policy))
         h = C.c_void_p()
         L.check(self.lib.b200q_engine_create(model.handle, C.byref(ecfg), C.byref(h)))
         self.handle = h
+        if len(stop_ids) > 1:
+            arr = (C.c_int32 * len(stop_ids))(*stop_ids)
+            L.check(self.lib.b200q_engine_set_stop_ids(h, arr, len(stop_ids)))
         self.cap = max_num_seqs
         self._ids = np.zeros(self.cap, dtype=np.int64)
         self._tok = np.zeros(self.cap, dtype=np.int32)

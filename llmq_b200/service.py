@@ -20,15 +20,15 @@ from . import lib as L
 
 
 class _Req:
-    __slots__ = ("slot", "prompt_ids", "max_new", "stop", "future", "text_len", "loop",
-                 "temperature", "seed")
+    __slots__ = ("slot", "prompt_ids", "max_new", "stop", "future", "loop",
+                 "temperature", "seed", "detok")
 
     def __init__(self, prompt_ids, max_new, stop, future, loop, temperature=0.0, seed=0):
         self.prompt_ids, self.max_new, self.stop = prompt_ids, max_new, stop
         self.future, self.loop = future, loop
         self.temperature, self.seed = temperature, seed
         self.slot = -1   # engine request id = row of the token table, assigned on the engine thread
-        self.text_len = 0
+        self.detok = None  # _StopScanner, only for requests that carry stop strings
 
 
 class _TokenTable:
@@ -78,6 +78,49 @@ class _TokenTable:
         return self.tok[slot, : self.n[slot]].tolist()
 
 
+class _StopScanner:
+    """Incremental detokenisation + stop-string scan of ONE request, the behaviour of vLLM's
+    detokenizer (vllm/v1/engine/detokenizer.py:95-165): every new token extends the text by the
+    characters it adds; only the new characters plus a hold-back of ``max(len(stop)) - 1`` are
+    searched (:86-87), and the output is cut before the earliest stop string.
+
+    Work per token is O(window), not O(generated length): the text of a new token is obtained by
+    decoding a short tail of ids (``prefix`` ids of context, as in vLLM's / HF's incremental
+    detokeniser) and taking what it adds over the same tail without the new token.  While the tail
+    ends in an incomplete UTF-8 sequence (U+FFFD) nothing is emitted, exactly like DecodeStream."""
+
+    PREFIX = 6  # ids of left context that settle spacing / byte-fallback merges
+
+    def __init__(self, stop: List[str], decode):
+        self.stop = stop
+        self.hold = max(len(s) for s in stop) - 1
+        self.decode = decode
+        self.ids: List[int] = []
+        self.text = ""          # emitted text so far
+        self.prefix_off = 0     # ids[prefix_off:read_off] = context already reflected in `text`
+        self.read_off = 0
+
+    def push(self, token: int) -> Optional[str]:
+        """append one token; returns the final (cut) text if a stop string completed, else None"""
+        self.ids.append(token)
+        ids = self.ids
+        prefix_text = self.decode(ids[self.prefix_off:self.read_off]) if self.read_off > self.prefix_off else ""
+        full = self.decode(ids[self.prefix_off:])
+        if full.endswith("\ufffd") or len(full) <= len(prefix_text):
+            return None  # an incomplete multi-byte character (or nothing new): wait for more ids
+        new = full[len(prefix_text):]
+        self.prefix_off = max(self.read_off, len(ids) - self.PREFIX)
+        self.read_off = len(ids)
+        start = max(0, len(self.text) - self.hold)
+        self.text += new
+        best = -1
+        for s in self.stop:
+            i = self.text.find(s, start)
+            if i >= 0 and (best < 0 or i < best):
+                best = i
+        return self.text[:best] if best >= 0 else None
+
+
 class GenerationService:
     """Engine thread + request table.  Pure host logic around llmq_b200.model.Engine; also used
     directly by bench.py (the same public call a worker makes)."""
@@ -107,6 +150,7 @@ class GenerationService:
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, name="b200q-engine", daemon=True)
         self.error: Optional[BaseException] = None
+        self.on_fatal = None   # callable(exc): the worker stops consuming when the engine thread dies
         self.tokens_out = 0
         self.jobs_done = 0
         self.first_submit_t: Optional[float] = None
@@ -180,16 +224,35 @@ class GenerationService:
 
     def _check_stop_strings(self, r: _Req) -> Optional[str]:
         """vLLM detokenizer semantics (vllm/v1/engine/detokenizer.py:131-143): after every new
-        token look for a stop string in the newly produced text; the output is cut before it."""
-        text = self.decode(self._table.tokens(r.slot))
-        start = max(0, r.text_len - max(len(s) for s in r.stop))
-        r.text_len = len(text)
-        best = -1
-        for s in r.stop:
-            i = text.find(s, start)
-            if i >= 0 and (best < 0 or i < best):
-                best = i
-        return text[:best] if best >= 0 else None
+        token look for a stop string in the newly produced text (plus the hold-back window); the
+        output is cut before it.  Incremental: see _StopScanner."""
+        n = int(self._table.n[r.slot])
+        sc = r.detok
+        cut = None
+        while len(sc.ids) < n and cut is None:  # normally exactly one new token
+            cut = sc.push(int(self._table.tok[r.slot, len(sc.ids)]))
+        return cut
+
+    def _admit(self, batch, r: _Req) -> None:
+        """engine thread: give the request a table row and hand it to the engine.  Anything wrong
+        with THIS request (oversized prompt, absurd max_tokens) fails this request only — as
+        ValueError, which the base class turns into log + ack/drop (ref:llmq/workers/base.py:228-235)."""
+        try:
+            limit = int(getattr(self.engine, "max_model_len", 0) or 0)
+            max_new = int(r.max_new)
+            if max_new < 1:
+                raise ValueError(f"max_tokens must be >= 1 (got {max_new})")
+            if limit > 0:  # the engine clamps to max_model_len - n_prompt anyway; never size rows beyond it
+                max_new = min(max_new, limit)
+            r.max_new = min(max_new, 2 ** 31 - 1)
+            r.slot = self._table.alloc(r.max_new, bool(r.stop))
+            if r.stop:
+                r.detok = _StopScanner(r.stop, self.decode)
+            self.engine.add_request(r.slot, r.prompt_ids, r.max_new, ignore_eos=False,
+                                    temperature=r.temperature, seed=r.seed)
+            self._reqs[r.slot] = r
+        except (ValueError, OverflowError, MemoryError) as e:  # un-servable job => dropped by the base class
+            self._finish(batch, r, exc=e if isinstance(e, ValueError) else ValueError(f"un-servable request: {e!r}"))
 
     def _run(self):
         eng = self.engine
@@ -198,8 +261,10 @@ class GenerationService:
                 import torch
 
                 torch.cuda.set_device(eng.model.device)  # this thread owns the CUDA context
+            r = None
             while not self._stop.is_set():
                 batch: dict = {}
+                r = None
                 # admit new requests
                 try:
                     block = not eng.has_work()
@@ -207,13 +272,8 @@ class GenerationService:
                     while True:
                         if self.first_submit_t is None:
                             self.first_submit_t = time.perf_counter()
-                        r.slot = self._table.alloc(max(int(r.max_new), 1), bool(r.stop))
-                        try:
-                            eng.add_request(r.slot, r.prompt_ids, r.max_new, ignore_eos=False,
-                                            temperature=r.temperature, seed=r.seed)
-                            self._reqs[r.slot] = r
-                        except ValueError as e:  # un-servable job => dropped by the base class
-                            self._finish(batch, r, exc=e)
+                        self._admit(batch, r)
+                        r = None
                         r = self._inbox.get_nowait()
                 except queue.Empty:
                     pass
@@ -242,13 +302,57 @@ class GenerationService:
                 for loop, items in batch.items():
                     loop.call_soon_threadsafe(self._deliver, items)
         except BaseException as e:  # surface engine failures to every waiter
-            self.error = e
+            self.error = e   # submit() refuses new work from here on
             batch = {}
-            for r in list(self._reqs.values()):
-                self._finish(batch, r, exc=RuntimeError(f"engine failure: {e!r}"))
+            err = RuntimeError(f"engine failure: {e!r}")
+            pending = list(self._reqs.values())
+            if r is not None and r.slot not in self._reqs:
+                pending.append(r)   # the request in hand when the failure hit
+            while True:             # ... and everything still queued behind it
+                try:
+                    pending.append(self._inbox.get_nowait())
+                except queue.Empty:
+                    break
+            for q in pending:
+                if not q.future.done():
+                    self._finish(batch, q, exc=err)
+            if self.on_fatal is not None:   # before the waiters wake up: they must see the worker stopping
+                try:
+                    self.on_fatal(e)
+                except Exception:
+                    pass
             for loop, items in batch.items():
-                loop.call_soon_threadsafe(self._deliver, items)
+                try:
+                    loop.call_soon_threadsafe(self._deliver, items)
+                except RuntimeError:   # that loop is already closed
+                    pass
             raise
+
+
+def collect_stop_ids(model_dir: str, spec, tokenizer) -> List[int]:
+    """Every token id that ends generation for this model, as vLLM derives it for the reference
+    worker: tokenizer.eos_token_id, plus every eos id of config.json, plus every eos id of
+    generation_config.json (vllm/sampling_params.py update_from_generation_config adds the latter
+    as stop_token_ids).  Llama-3.x-Instruct: [128001, 128008, 128009]; gemma-2-it: [1, 107]."""
+    import json
+
+    ids: List[int] = []
+
+    def add(v):
+        for x in (v if isinstance(v, (list, tuple)) else [v]):
+            if x is not None and int(x) not in ids:
+                ids.append(int(x))
+
+    add(getattr(tokenizer, "eos_token_id", None))
+    add(list(spec.eos_token_ids) or spec.eos_token_id)
+    gpath = os.path.join(model_dir, "generation_config.json")
+    if os.path.exists(gpath):
+        try:
+            with open(gpath) as f:
+                add(json.load(f).get("eos_token_id"))
+        except (OSError, ValueError):
+            pass
+    return [i for i in ids if 0 <= i < spec.vocab]
 
 
 def build_service(model_name: str, *, max_num_seqs: Optional[int], max_model_len: Optional[int],
@@ -263,7 +367,11 @@ def build_service(model_name: str, *, max_num_seqs: Optional[int], max_model_len
     spec, model_dir = resolve_model(model_name)
     device = torch.device("cuda", torch.cuda.current_device())
     max_num_seqs = max_num_seqs or int(os.environ.get("B200Q_MAX_NUM_SEQS", "256"))
-    max_model_len = min(max_model_len or int(os.environ.get("B200Q_MAX_MODEL_LEN", "4096")),
+    # VLLM_MAX_MODEL_LEN unset: the model's own context length, like vLLM (the reference leaves it
+    # to the engine, ref:llmq/workers/vllm_worker.py:119-120) — capped by what the KV pool can hold
+    # (NativeModel) instead of refusing to start
+    env_len = os.environ.get("B200Q_MAX_MODEL_LEN")
+    max_model_len = min(max_model_len or (int(env_len) if env_len else spec.max_position_embeddings),
                         spec.max_position_embeddings)
     budget = max_num_batched_tokens or int(os.environ.get("B200Q_MAX_NUM_BATCHED_TOKENS", "4096"))
     budget = max(budget, 16)
@@ -272,19 +380,24 @@ def build_service(model_name: str, *, max_num_seqs: Optional[int], max_model_len
 
         weights = random_engine_weights(spec, seed, device)
         tokenizer = build_tokenizer(spec.vocab)
-        eos = special_token_ids(spec.vocab)["<|end_of_text|>"]
+        stop_ids = [special_token_ids(spec.vocab)["<|end_of_text|>"]]
     else:
         from transformers import AutoTokenizer
 
         weights = fuse_hf_weights(spec, load_hf_state_dict(model_dir))
         tokenizer = AutoTokenizer.from_pretrained(model_dir)
-        eos = spec.eos_token_id if spec.eos_token_id is not None else tokenizer.eos_token_id
+        stop_ids = collect_stop_ids(model_dir, spec, tokenizer)
     model = NativeModel(spec, weights, max_tokens=budget, max_seqs=max_num_seqs,
                         max_model_len=max_model_len, gpu_memory_utilization=gpu_memory_utilization,
                         device=device, num_blocks=num_blocks)
     if logger:
+        if model.max_model_len < max_model_len:
+            logger.warning(f"b200q: max_model_len reduced from {max_model_len} to {model.max_model_len} "
+                           f"(KV pool of {model.num_blocks} blocks / attention window); longer prompts are dropped")
         logger.info(f"b200q model {spec.name}: {model.num_blocks} KV blocks of 16 tokens, "
-                    f"max_num_seqs={max_num_seqs}, token budget={budget}, max_model_len={max_model_len}")
+                    f"max_num_seqs={max_num_seqs}, token budget={budget}, max_model_len={model.max_model_len}, "
+                    f"stop ids={stop_ids}")
     engine = Engine(model, max_num_seqs=max_num_seqs, max_num_batched_tokens=budget,
-                    max_model_len=max_model_len, eos_token_id=eos)
+                    max_model_len=model.max_model_len, eos_token_id=stop_ids or None)
+    eos = stop_ids[0] if stop_ids else None
     return GenerationService(engine, tokenizer, eos)

@@ -61,8 +61,16 @@ class B200Worker(BaseWorker):
         self.service = build_service(
             self.model_name, max_num_seqs=cfg.vllm_max_num_seqs, max_model_len=cfg.vllm_max_model_len,
             gpu_memory_utilization=cfg.vllm_gpu_memory_utilization, logger=self.logger)
+        self.service.on_fatal = self._engine_died
         self.service.start()
         self.logger.info("b200q engine initialized successfully")
+
+    def _engine_died(self, exc: BaseException) -> None:
+        """engine thread: the native engine is gone.  Stop consuming (BaseWorker.run leaves its idle
+        loop when `running` is False and runs cleanup) so the un-acked jobs go back to the queue for
+        the other workers instead of being rejected and redelivered to this one in a hot loop."""
+        self.logger.error(f"b200q engine thread died: {exc!r}; stopping worker {self.worker_id}")
+        self.running = False
 
     def build_prompt(self, job: Job) -> str:
         """prompt text exactly as the reference builds it (vllm_worker.py:168-180)"""
@@ -103,8 +111,11 @@ class B200Worker(BaseWorker):
         return text
 
     async def _cleanup_processor(self) -> None:
+        """ref:llmq/workers/vllm_worker.py:197-201 drops the engine; here that means: stop the engine
+        thread, destroy the native handles and return weights / KV pool / workspace to the driver
+        (NativeModel.close empties torch's cache), so another engine can be built in this process"""
         if self.service is not None:
-            self.service.stop()
-            self.service.engine.close()
-            self.service.engine.model.close()
-            self.service = None
+            svc, self.service = self.service, None
+            svc.stop()
+            svc.engine.close()
+            svc.engine.model.close()

@@ -418,3 +418,176 @@ def test_reference_quirks_are_replicated_not_fixed(patched):
         await w._cleanup_processor()
 
     asyncio.run(main())
+
+
+def test_absurd_max_tokens_fails_one_job_not_the_engine_thread(monkeypatch):
+    """a job carrying max_tokens=3e9 used to raise MemoryError while sizing its token-table
+    row, inside the engine thread, which killed generation for every request.  It is clamped to
+    the engine's max_model_len now, and any per-request admission failure surfaces as ValueError
+    for that request only (=> ack/drop by the base class), the others complete."""
+    from llmq_b200.fixtures import DryRunEngine
+
+    tok = build_tokenizer(VOCAB)
+    eng = DryRunEngine(VOCAB, max_num_seqs=8, max_num_batched_tokens=64, max_model_len=64, num_blocks=64)
+    svc = S.GenerationService(eng, tok, None)
+    svc.start()
+
+    async def main():
+        loop = asyncio.get_running_loop()
+        futs = [svc.submit([5, 6, 7], 3_000_000_000, None, loop),      # clamped: runs to max_model_len
+                svc.submit([9], 4, None, loop),
+                svc.submit([9], 0, None, loop),                        # max_tokens < 1: this job only
+                svc.submit([9], 10 ** 30, None, loop)]
+        return await asyncio.gather(*futs, return_exceptions=True)
+
+    res = asyncio.run(main())
+    svc.stop()
+    assert svc.error is None, svc.error
+    assert res[0][1] == 64 - 3 and res[1][1] == 4            # (text, n_tokens)
+    assert isinstance(res[2], ValueError)
+    assert res[3][1] == 63
+    assert svc._table.tok.shape[1] <= 64                     # rows never sized beyond max_model_len
+
+
+def test_fatal_engine_error_resolves_queued_and_in_hand_requests(monkeypatch):
+    """when the engine thread dies, requests still in the inbox and the one being
+    admitted must get their futures resolved too (their AMQP messages would otherwise stay un-acked
+    for ever), and the worker is told to stop consuming."""
+    tok = build_tokenizer(VOCAB)
+
+    class DyingEngine(FakeEngine):
+        def add_request(self, rid, ids, max_new, **kw):
+            if rid >= 1:
+                raise OSError("cuda context lost")   # not a per-request error
+            return super().add_request(rid, ids, max_new, **kw)
+
+    eng = DyingEngine(vocab=VOCAB, max_num_seqs=4, max_model_len=64)
+    svc = S.GenerationService(eng, tok, None)
+    fatal = []
+    svc.on_fatal = fatal.append
+
+    async def main():
+        loop = asyncio.get_running_loop()
+        futs = [svc.submit([5 + i], 4, None, loop) for i in range(6)]   # all queued before the thread starts
+        svc.start()
+        return await asyncio.wait_for(asyncio.gather(*futs, return_exceptions=True), 10)
+
+    res = asyncio.run(main())
+    assert all(isinstance(r, RuntimeError) and "engine failure" in str(r) for r in res), res
+    assert len(fatal) == 1 and isinstance(svc.error, OSError)
+    with pytest.raises(RuntimeError, match="engine thread died"):
+        svc.submit([1], 1, None, None)
+
+
+def test_worker_stops_consuming_when_the_engine_dies(patched):
+    made, tok = patched
+
+    async def main():
+        w = B200Worker("random:llama-3-8b", "dq", tensor_parallel_size=1)
+        await w._initialize_processor()
+        w.running = True
+        made["engine"].step = lambda: (_ for _ in ()).throw(OSError("xid 79"))
+        with pytest.raises(RuntimeError):
+            await w._process_job(Job(id="a", prompt="w9"))
+        assert w.running is False
+        await w._cleanup_processor()
+
+    asyncio.run(main())
+
+
+def test_stop_scanner_is_incremental_and_matches_whole_text_search():
+    """stop strings were found by re-decoding the whole output after every
+    token (O(n^2)).  _StopScanner decodes a bounded tail per token; on an 8192-token output (the
+    reference's default VLLM_MAX_TOKENS) it must (a) find the same cut as a search of the full
+    text, (b) call decode on short windows only."""
+    import numpy as np
+
+    tok = build_tokenizer(VOCAB)
+    backend = tok.backend_tokenizer
+    calls = []
+
+    def decode(ids):
+        calls.append(len(ids))
+        return backend.decode(ids, skip_special_tokens=True)
+
+    rng = np.random.default_rng(0)
+    ids = rng.integers(10, 900, size=8192).tolist()
+    # a stop string that spans two tokens, completed by the very last token only
+    stop = [f"w{ids[-2]} w{ids[-1]}", "never-there"]
+    ids_before = ids[:-2]
+    while stop[0] in backend.decode(ids_before + [ids[-2]], skip_special_tokens=True):
+        ids[-2] = (ids[-2] + 1) % 900 + 10  # keep the only match at the end
+        stop[0] = f"w{ids[-2]} w{ids[-1]}"
+    sc = S._StopScanner(stop, decode)
+    cut = None
+    for k, t in enumerate(ids):
+        cut = sc.push(t)
+        if cut is not None:
+            break
+    full = backend.decode(ids, skip_special_tokens=True)
+    assert k == len(ids) - 1, "stop must complete on the last token"
+    assert cut == full[: full.find(stop[0])]
+    assert max(calls) <= 2 * S._StopScanner.PREFIX + 2, f"decode window grew to {max(calls)} ids"
+    # special tokens never reach the text (skip_special_tokens) and never match
+    sc2 = S._StopScanner(["<|end_of_text|>"], decode)
+    from llmq_b200.fixtures import special_token_ids
+    assert sc2.push(special_token_ids(VOCAB)["<|end_of_text|>"]) is None and sc2.text == ""
+
+
+def test_every_eos_id_of_the_model_ends_generation(tmp_path):
+    """ADVICE r1: instruct models list several EOS ids (Llama-3.x-Instruct: 128001/128008/128009;
+    gemma-2-it adds <end_of_turn> in generation_config.json); vLLM stops on all of them, so must
+    the native engine — otherwise chat jobs run on to VLLM_MAX_TOKENS."""
+    from llmq_b200.fixtures import DryRunEngine
+    from llmq_b200.model import ModelSpec
+
+    cfg = {"architectures": ["LlamaForCausalLM"], "hidden_size": 64, "num_hidden_layers": 1,
+           "num_attention_heads": 2, "intermediate_size": 128, "vocab_size": VOCAB,
+           "eos_token_id": [901, 908, 909], "bos_token_id": 900}
+    spec = ModelSpec.from_hf_config(cfg)
+    assert spec.eos_token_id == 901 and spec.eos_token_ids == (901, 908, 909)
+    (tmp_path / "generation_config.json").write_text(json.dumps({"eos_token_id": [901, 107]}))
+
+    class Tok:
+        eos_token_id = 902
+
+    assert S.collect_stop_ids(str(tmp_path), spec, Tok()) == [902, 901, 908, 909, 107]
+    # the dry-run model counts up: prompt ending in 105 => 106, 107 (stop id) ...
+    eng = DryRunEngine(VOCAB, max_num_seqs=4, max_num_batched_tokens=32, max_model_len=64, num_blocks=16,
+                       eos_token_id=[902, 901, 908, 909, 107])
+    eng.add_request(0, [5, 105], 30)
+    eng.add_request(1, [5, 905], 30)
+    eng.add_request(2, [5, 905], 30, ignore_eos=True)
+    out = {0: [], 1: [], 2: []}
+    while eng.has_work():
+        ids, toks, flags = eng.step()
+        for i, t in zip(ids.tolist(), toks.tolist()):
+            out[i].append(t)
+    assert out[0] == [106, 107] and out[1] == [906, 907, 908] and len(out[2]) == 30
+    eng.close()
+
+
+def test_default_max_model_len_is_the_models_own(monkeypatch):
+    """with VLLM_MAX_MODEL_LEN unset the reference leaves the context length to vLLM
+    (= max_position_embeddings), not 4096; prompts of 4096+ tokens on an 8k model must be served"""
+    import llmq_b200.model as M
+    seen = {}
+
+    class StopHere(Exception):
+        pass
+
+    def fake_native_model(spec, weights, **kw):
+        seen.update(kw)
+        raise StopHere
+
+    monkeypatch.setattr(M, "NativeModel", fake_native_model)
+    monkeypatch.setattr(S.L, "require_device", lambda: None)
+    import torch
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.delenv("B200Q_MAX_MODEL_LEN", raising=False)
+    with pytest.raises(StopHere):
+        S.build_service("random:llama-3-8b", max_num_seqs=4, max_model_len=None, gpu_memory_utilization=0.5)
+    assert seen["max_model_len"] == 8192
+    with pytest.raises(StopHere):
+        S.build_service("random:llama-3-8b", max_num_seqs=4, max_model_len=1024, gpu_memory_utilization=0.5)
+    assert seen["max_model_len"] == 1024

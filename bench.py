@@ -395,7 +395,9 @@ def run_native(args):
     spec = model.spec
     S, J, W, K = args.max_num_seqs, args.jobs, args.warmup, args.steps
     K_e = min(K, args.e2e_steps)
-    W_e = min(W, 2)
+    # e2e tokens are counted on the host, per completed job: the warm-up has to flush the ramp cohort
+    # (max_num_seqs jobs with staggered, i.e. shorter, outputs) before the clock starts
+    W_e = 0 if W == 0 else max(2, -(-S // J))
     # canonical seeded job stream, this rank's shard (queue-sharding by job index).  Each arm needs:
     # the ramp cohort that fills the empty engine + its timed steps + a backlog that keeps the queue
     # non-empty until the clock stops (the worker is never starved: a 100k-prompt queue behind it)

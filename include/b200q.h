@@ -52,6 +52,12 @@ int b200q_device_check(void);
 /* K1  embedding gather: out[t,:] = table[ids[t],:]            (vLLM VocabParallelEmbedding) */
 int b200q_embed(const int32_t* ids_dev, const void* table_dev, void* out_dev,
                 int T, int H, void* stream);
+/* same, where ids[t] < 0 stands for prev_out_dev[-1 - ids[t]] — a token the previous step sampled
+ * and left on the device (the engine enqueues step k+1 before reading step k's ids back, as
+ * vLLM's async scheduling does: vllm/v1/worker/gpu_model_runner.py prev_sampled_token_ids);
+ * scale > 0 and != 1 multiplies the row (Gemma normaliser), 0 = plain gather */
+int b200q_embed_ex(const int32_t* ids_dev, const int32_t* prev_out_dev, const void* table_dev,
+                   void* out_dev, int T, int H, float scale, void* stream);
 
 /* K2  RMSNorm: y = bf16(bf16(x * rsqrt(mean(x^2)+eps)) * w)      (vllm/ir/ops/layernorm.py:9-21) */
 int b200q_rmsnorm(const void* x_dev, const void* w_dev, void* y_dev,
@@ -216,6 +222,9 @@ typedef struct b200q_batch {
   /* host-side bookkeeping for the profiler (algorithmic work of this step's attention) */
   int64_t sum_ctx_dec;          /* sum of ctx_lens over the decode sequences                    */
   int64_t prefill_flops_per_layer; /* causal QK^T + PV flops of the prefill tiles, one layer     */
+  /* async stepping: token_ids[t] < 0 stands for prev_out_ids[-1 - token_ids[t]], a token the
+   * previous step sampled and the host has not read back yet; NULL when no id is negative      */
+  const int32_t* prev_out_ids;
 } b200q_batch;
 
 int b200q_model_create(const b200q_model_config* cfg, b200q_model_t* out);
@@ -315,10 +324,17 @@ int b200q_engine_add_request_sampled(b200q_engine_t e, int64_t req_id, const int
  * update_from_generation_config), which the reference worker inherits (vllm_worker.py:161-165). */
 int b200q_engine_set_stop_ids(b200q_engine_t e, const int32_t* ids, int32_t n);
 int b200q_engine_abort(b200q_engine_t e, int64_t req_id);
+/* Async stepping (default on; env B200Q_ASYNC=0 or on=0 turns it off): b200q_engine_step enqueues
+ * step k+1 BEFORE it reads step k's sampled ids back, so the events a call returns are those of
+ * the step enqueued by the PREVIOUS call, and b200q_engine_has_work stays 1 while a step is in
+ * flight.  Off: every call returns the events of the step it ran (one sync per step).  Token
+ * sequences are identical in both modes.  Only while no step is in flight (B200Q_ESTATE else). */
+int b200q_engine_set_async(b200q_engine_t e, int32_t on);
 /* 1 if any request is waiting or running */
 int b200q_engine_has_work(b200q_engine_t e);
-/* run one scheduler step + forward; writes up to cap (req_id, token, flags) events for the
- * tokens produced this step.  cap must be >= max_num_seqs. */
+/* run one scheduler step + forward; writes up to cap (req_id, token, flags) events — those of this
+ * step (sync mode) or of the previously enqueued step (async mode, see b200q_engine_set_async).
+ * cap must be >= max_num_seqs. */
 int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_tokens,
                       int32_t* out_flags, int32_t cap, int32_t* n_out);
 int b200q_engine_get_stats(b200q_engine_t e, b200q_engine_stats* out);

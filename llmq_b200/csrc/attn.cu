@@ -105,6 +105,56 @@ __device__ __forceinline__ void pv_page(uint32_t v_s, const float (&p)[BS / 8][4
   }
 }
 
+// Decode: O^T(D x 8 heads) += V^T(D x BS tokens) . P^T(BS x 8 heads).  With the G <= 8 heads on
+// the N side the accumulator has no unused rows (D/16 tiles x 4 registers instead of D/8 x 4) and
+// PV needs D/16 MMAs per page instead of D/8.  The S accumulators of qk_page<false> (rows = heads,
+// cols = tokens) are exactly the B fragments of P^T: b0 = tokens 0-7, b1 = tokens 8-15.  A = V^T
+// comes from the swizzled V page with ldmatrix.trans: matrix i of the x4 load covers tokens
+// 8*(i>>1).. and the 16-byte chunk 2*tile + (i&1).  (lane-accurate check: tools/emu/)
+template <int D, int BS>
+__device__ __forceinline__ void pv_page_t(uint32_t v_s, const float (&p)[BS / 8][4],
+                                          float (&o)[D / 16][4], int lane) {
+  static_assert(BS == 16, "one 16-token page = one k-step of the PV MMA");
+  using G_ = Geo<D, BS>;
+  const uint32_t b0 = pack_bf16x2(p[0][0], p[0][1]);
+  const uint32_t b1 = pack_bf16x2(p[1][0], p[1][1]);
+  const int mi = lane >> 3;
+  const int token = (mi >> 1) * 8 + (lane & 7);
+  const uint32_t row_addr = v_s + token * G_::ROW_BYTES;
+#pragma unroll
+  for (int tile = 0; tile < D / 16; ++tile) {
+    const int chunk = 2 * tile + (mi & 1);
+    uint32_t a0, a1, a2, a3;
+    ldsm_x4_t(row_addr + ((chunk ^ (token & 7)) << 4), a0, a1, a2, a3);
+    mma_bf16_16816(o[tile], a0, a1, a2, a3, b0, b1);
+  }
+}
+
+// O^T accumulators hold heads 2(lane&3), +1 in their columns; a per-head value (alpha, 1/l) lives
+// in the lanes of row `head` of the S layout, i.e. lanes 4*head .. 4*head+3
+__device__ __forceinline__ void per_head_pair(float v, int lane, float& h0, float& h1) {
+  const int cq = (lane & 3) * 2;
+  h0 = __shfl_sync(0xffffffffu, v, cq * 4);
+  h1 = __shfl_sync(0xffffffffu, v, cq * 4 + 4);
+}
+
+template <int D>
+__device__ __forceinline__ void scale_ot(float (&o)[D / 16][4], float h0, float h1) {
+#pragma unroll
+  for (int i = 0; i < D / 16; ++i) {
+    o[i][0] *= h0;
+    o[i][1] *= h1;
+    o[i][2] *= h0;
+    o[i][3] *= h1;
+  }
+}
+
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t v) {
+  uint32_t r;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
 // zero rows [n_valid, BS) of a V page in shared memory (whole warp), so that masked
 // probabilities (exactly 0) never meet stale NaN/Inf bit patterns in the PV mma.
 template <int D, int BS>
@@ -207,9 +257,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
     }
   }
 
-  float o[D / 8][4];
+  float o[D / 16][4];  // O^T tiles: [dim = 16 i + lane/4 (+8)][head = 2(lane&3), +1]
 #pragma unroll
-  for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  for (int i = 0; i < D / 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m = -INFINITY, l = 0.f;
 
   for (int k = 0; k < my_n; ++k) {
@@ -248,12 +298,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
     }
     l = l * alpha + psum;
     m = m_new;
-#pragma unroll
-    for (int i = 0; i < D / 8; ++i) {
-      o[i][0] *= alpha;
-      o[i][1] *= alpha;
-    }
-    pv_page<D, BS, false>(v_s, s, o, lane);
+    float a0, a1;
+    per_head_pair(alpha, lane, a0, a1);
+    scale_ot<D>(o, a0, a1);
+    pv_page_t<D, BS>(v_s, s, o, lane);
     __syncwarp();
     if (k + DEC_STAGES < my_n) issue(k + DEC_STAGES);
   }
@@ -262,18 +310,25 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
   l += __shfl_xor_sync(0xffffffffu, l, 1);
   l += __shfl_xor_sync(0xffffffffu, l, 2);
   {
-    const int r = lane >> 2;
-    float* mo = merge + (warp * 8 + r) * (D + 2);
-    if (r < G) {
+    // partial state of this warp: O^T columns are heads 2(lane&3), +1; m and l sit in the S layout
+    const int r = lane >> 2, h0 = (lane & 3) * 2;
+    float* m0 = merge + (warp * 8 + h0) * (D + 2);
+    float* m1 = m0 + (D + 2);
 #pragma unroll
-      for (int i = 0; i < D / 8; ++i) {
-        mo[i * 8 + (lane & 3) * 2] = o[i][0];
-        mo[i * 8 + (lane & 3) * 2 + 1] = o[i][1];
+    for (int i = 0; i < D / 16; ++i) {
+      if (h0 < G) {
+        m0[i * 16 + r] = o[i][0];
+        m0[i * 16 + 8 + r] = o[i][2];
       }
-      if ((lane & 3) == 0) {
-        mo[D] = m;
-        mo[D + 1] = l;
+      if (h0 + 1 < G) {
+        m1[i * 16 + r] = o[i][1];
+        m1[i * 16 + 8 + r] = o[i][3];
       }
+    }
+    if (r < G && (lane & 3) == 0) {
+      float* mo = merge + (warp * 8 + r) * (D + 2);
+      mo[D] = m;
+      mo[D + 1] = l;
     }
   }
   __syncthreads();
@@ -430,9 +485,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
       n_ctx = max(__ldg(ctx_lens + (item + n_warps) / n_kv), 1);
       load_q(item + n_warps, qn);
     }
-    float o[D / 8][4];
+    float o[D / 16][4];  // O^T tiles: [dim = 16 i + lane/4 (+8)][head = 2(lane&3), +1]
 #pragma unroll
-    for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    for (int i = 0; i < D / 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m = -INFINITY, l = 0.f;
     for (int p = lo / BS; p < n_pages; ++p) {
       const int st = consumed % DEC_STAGES;
@@ -466,25 +521,29 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
       }
       l = l * alpha + psum;
       m = m_new;
-#pragma unroll
-      for (int i = 0; i < D / 8; ++i) {
-        o[i][0] *= alpha;
-        o[i][1] *= alpha;
-      }
-      pv_page<D, BS, false>(v_s, s, o, lane);
+      float a0, a1;
+      per_head_pair(alpha, lane, a0, a1);
+      scale_ot<D>(o, a0, a1);
+      pv_page_t<D, BS>(v_s, s, o, lane);
       __syncwarp();
       ++consumed;
       issue_next();  // refill the stage that was just drained
     }
     l += __shfl_xor_sync(0xffffffffu, l, 1);
     l += __shfl_xor_sync(0xffffffffu, l, 2);
-    if (r < G) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      const int seq = item / n_kv, kvh = item % n_kv;
-      bf16* orow = out + (long long)seq * n_q * D + (long long)(kvh * G + r) * D;
+    float i0, i1;
+    per_head_pair(l > 0.f ? 1.f / l : 0.f, lane, i0, i1);
+    const int seq = item / n_kv, kvh = item % n_kv;
+    bf16* orow = out + (long long)seq * n_q * D + (long long)(kvh * G + r) * D;
 #pragma unroll
-      for (int i = 0; i < D / 8; ++i)
-        *reinterpret_cast<uint32_t*>(orow + i * 8 + cq) = pack_bf16x2(o[i][0] * inv, o[i][1] * inv);
+    for (int i = 0; i < D / 16; ++i) {
+      // transpose the bf16 tile halves back to [head = lane/4][dims 2(lane&3), +1] for 4-byte stores
+      const uint32_t d0 = movmatrix_trans(pack_bf16x2(o[i][0] * i0, o[i][1] * i1));
+      const uint32_t d1 = movmatrix_trans(pack_bf16x2(o[i][2] * i0, o[i][3] * i1));
+      if (r < G) {
+        *reinterpret_cast<uint32_t*>(orow + i * 16 + cq) = d0;
+        *reinterpret_cast<uint32_t*>(orow + i * 16 + 8 + cq) = d1;
+      }
     }
   }
 }

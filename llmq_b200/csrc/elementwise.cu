@@ -26,20 +26,32 @@ int tuning_epoch() { return __atomic_load_n(&g_epoch, __ATOMIC_RELAXED); }
 // ------------------------------------------------------------------------------------------
 // K1 embedding gather.  One warp per 512 B (32 lanes x 16 B); grid-stride over (token, chunk).
 // ------------------------------------------------------------------------------------------
+// A negative id is an indirection into `prev_out`, the sampled ids of the PREVIOUS forward step
+// (id = prev_out[-1 - ids[t]]): the engine enqueues step k+1 before it has read step k's tokens
+// back, so a decode row's input token is still on the device (engine.cu, async stepping).
+__device__ __forceinline__ int resolve_token(const int32_t* __restrict__ ids,
+                                             const int32_t* __restrict__ prev_out, int t) {
+  int id = __ldg(ids + t);
+  if (id < 0) id = prev_out[-1 - id];  // plain load: written by the previous step's sampler
+  return id;
+}
+
 __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ ids,
+                                                    const int32_t* __restrict__ prev_out,
                                                     const uint4* __restrict__ table,
                                                     uint4* __restrict__ out, int T, int chunks) {
   long long total = (long long)T * chunks;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int t = (int)(i / chunks), c = (int)(i % chunks);
-    int id = __ldg(ids + t);
+    int id = resolve_token(ids, prev_out, t);
     out[i] = ld_nc_v4(table + (long long)id * chunks + c);
   }
 }
 
 // Gemma: out = bf16(table[id] * scale) (the normaliser sqrt(H), itself rounded to bf16 by the host)
 __global__ void __launch_bounds__(256) embed_scaled_kernel(const int32_t* __restrict__ ids,
+                                                           const int32_t* __restrict__ prev_out,
                                                            const uint4* __restrict__ table,
                                                            uint4* __restrict__ out, int T, int chunks,
                                                            float scale) {
@@ -47,7 +59,7 @@ __global__ void __launch_bounds__(256) embed_scaled_kernel(const int32_t* __rest
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int t = (int)(i / chunks), c = (int)(i % chunks);
-    int id = __ldg(ids + t);
+    int id = resolve_token(ids, prev_out, t);
     uint4 a = ld_nc_v4(table + (long long)id * chunks + c);
     uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
 #pragma unroll
@@ -531,25 +543,30 @@ int b200q_device_check(void) {
   return B200Q_OK;
 }
 
-int b200q_embed(const int32_t* ids, const void* table, void* out, int T, int H, void* stream) {
+int b200q_embed_ex(const int32_t* ids, const int32_t* prev_out, const void* table, void* out, int T,
+                   int H, float scale, void* stream) {
   B200Q_CHECK_ARG(T >= 0 && H > 0 && H % 8 == 0, "embed: bad shape T=%d H=%d", T, H);
   if (T == 0) return B200Q_OK;
   int chunks = H / 8;
-  embed_kernel<<<grid_for((long long)T * chunks, 256), 256, 0, as_stream(stream)>>>(
-      ids, (const uint4*)table, (uint4*)out, T, chunks);
+  if (scale > 0.f && scale != 1.f)
+    embed_scaled_kernel<<<grid_for((long long)T * chunks, 256), 256, 0, as_stream(stream)>>>(
+        ids, prev_out, (const uint4*)table, (uint4*)out, T, chunks, scale);
+  else
+    embed_kernel<<<grid_for((long long)T * chunks, 256), 256, 0, as_stream(stream)>>>(
+        ids, prev_out, (const uint4*)table, (uint4*)out, T, chunks);
   B200Q_LAUNCH_CHECK();
   return B200Q_OK;
 }
 
+int b200q_embed(const int32_t* ids, const void* table, void* out, int T, int H, void* stream) {
+  return b200q_embed_ex(ids, nullptr, table, out, T, H, 0.f, stream);
+}
+
 int b200q_embed_scaled(const int32_t* ids, const void* table, void* out, int T, int H, float scale,
                        void* stream) {
-  B200Q_CHECK_ARG(T >= 0 && H > 0 && H % 8 == 0, "embed_scaled: bad shape T=%d H=%d", T, H);
-  if (T == 0) return B200Q_OK;
-  int chunks = H / 8;
-  embed_scaled_kernel<<<grid_for((long long)T * chunks, 256), 256, 0, as_stream(stream)>>>(
-      ids, (const uint4*)table, (uint4*)out, T, chunks, scale);
-  B200Q_LAUNCH_CHECK();
-  return B200Q_OK;
+  B200Q_CHECK_ARG(scale > 0.f, "embed_scaled: scale must be positive");
+  if (scale == 1.f) return b200q_embed_ex(ids, nullptr, table, out, T, H, 0.f, stream);
+  return b200q_embed_ex(ids, nullptr, table, out, T, H, scale, stream);
 }
 
 int b200q_gemma_rmsnorm(const void* x, const void* w, void* y, int T, int H, float eps,

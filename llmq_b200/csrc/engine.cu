@@ -13,6 +13,16 @@
 // int32 metadata (token ids, positions, slot mapping, context lengths, prefill q-tiles, sample
 // rows, block table), ships it with one H2D copy, runs the forward on the engine's stream and
 // reads back the sampled ids with one D2H copy.
+//
+// Async stepping (default; B200Q_ASYNC=0 turns it off): step k+1 is scheduled and enqueued while
+// step k still runs on the GPU — what vLLM calls async scheduling.  The scheduler only needs to
+// know THAT a running request gets one more token, not which: the token's place in the sequence
+// is held by a placeholder, and the row that consumes it in step k+1 carries a negative token id
+// that the embedding kernel resolves against step k's sampled ids, still on the device
+// (b200q_batch.prev_out_ids).  Step k's ids are read back after step k+1 has been enqueued, so the
+// GPU never waits for the host's scheduling / launch / Python turn-around.  The cost: a request
+// that samples a stop id in step k has already been given one more (discarded) token in step k+1.
+// Length stops are known when a step is scheduled and cost nothing.
 #include <stdlib.h>
 #include <string.h>
 
@@ -44,8 +54,28 @@ struct Request {
   std::vector<int32_t> blocks;
   float temperature = 0.f;      // 0 = greedy
   uint64_t seed = 0;
-  int32_t n_sched = 0;          // tokens scheduled in the current step
-  int32_t sample_slot = -1;     // index into out_ids for this step, or -1
+  int32_t n_sched = 0;          // tokens scheduled in the step being built
+  // async stepping: tokens[pending_pos] is a placeholder (-1) for the token an in-flight step is
+  // sampling into out_ids[pending_slot]; -1 = no unresolved token
+  int32_t pending_pos = -1;
+  int32_t pending_slot = -1;
+  int32_t refs = 0;             // in-flight steps that hold this request (0..2)
+  bool dead = false;            // finished / aborted while a later step still holds it: no more events
+};
+
+// one scheduled request of an in-flight step
+struct StepEntry {
+  Request* r;
+  int32_t sample_slot;   // index into the step's out_ids, or -1 (mid-prompt chunk)
+  int32_t token_pos;     // position in r->tokens the sampled token belongs to
+  bool finished_len;     // the request reached max_new / max_model_len with this token
+};
+
+struct InFlightStep {
+  bool active = false;
+  int buf = 0;           // which pinned metadata / output buffer the step uses
+  int n_sample = 0;
+  std::vector<StepEntry> entries;
 };
 
 }  // namespace
@@ -64,11 +94,19 @@ struct b200q_engine {
   std::vector<int32_t> free_blocks;
   int32_t total_blocks = 0;
 
-  int32_t* h_meta = nullptr;  // pinned
+  // pinned host buffers are double-buffered (the host fills step k+1's while step k's H2D copy /
+  // D2H read-back may still be pending); the device copies are single: everything is stream-ordered
+  int32_t* h_meta_buf[2] = {nullptr, nullptr};
+  int32_t* h_meta = nullptr;  // = h_meta_buf[buffer of the step being built]
   int32_t* d_meta = nullptr;
   int64_t meta_cap = 0;       // int32 elements
-  int32_t* h_out = nullptr;   // pinned
+  int32_t* h_out_buf[2] = {nullptr, nullptr};
   int32_t* d_out = nullptr;
+  cudaEvent_t done_ev[2] = {nullptr, nullptr};
+  bool async_steps = true;    // B200Q_ASYNC
+  int next_buf = 0;
+  InFlightStep inflight;      // the step running on the GPU while the next one is scheduled
+  int32_t prev_n_sample = 0;  // sample slots of the in-flight step (bounds the negative token ids)
 
   b200q_engine_stats stats{};
   // every token id that ends a request (cfg.eos_token_id plus b200q_engine_set_stop_ids):
@@ -162,10 +200,15 @@ int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b20
                 S * (int64_t)((e->max_blocks_per_seq + 7) & ~7) + 64;
   cudaError_t ce;
   if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (ce = cudaMallocHost(&e->h_meta, e->meta_cap * 4)) != cudaSuccess ||
+      (ce = cudaMallocHost(&e->h_meta_buf[0], e->meta_cap * 4)) != cudaSuccess ||
+      (ce = cudaMallocHost(&e->h_meta_buf[1], e->meta_cap * 4)) != cudaSuccess ||
       (ce = cudaMalloc(&e->d_meta, e->meta_cap * 4)) != cudaSuccess ||
-      (ce = cudaMallocHost(&e->h_out, S * 4)) != cudaSuccess ||
-      (ce = cudaMalloc(&e->d_out, S * 4)) != cudaSuccess) {
+      (ce = cudaMallocHost(&e->h_out_buf[0], S * 4)) != cudaSuccess ||
+      (ce = cudaMallocHost(&e->h_out_buf[1], S * 4)) != cudaSuccess ||
+      (ce = cudaMalloc(&e->d_out, S * 4)) != cudaSuccess ||
+      (ce = cudaMemset(e->d_out, 0, S * 4)) != cudaSuccess ||
+      (ce = cudaEventCreateWithFlags(&e->done_ev[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (ce = cudaEventCreateWithFlags(&e->done_ev[1], cudaEventDisableTiming)) != cudaSuccess) {
     set_error("engine_create: CUDA allocation failed: %s", cudaGetErrorString(ce));
     b200q_engine_destroy(e);
     return B200Q_ECUDA;
@@ -173,6 +216,8 @@ int b200q_engine_create(b200q_model_t model, const b200q_engine_config* cfg, b20
   {
     const char* v = getenv("B200Q_CUDA_GRAPHS");
     e->use_graphs = !(v && v[0] == '0');
+    v = getenv("B200Q_ASYNC");
+    e->async_steps = !(v && v[0] == '0');
   }
   // weights / KV were produced on other streams (torch); make them visible before first use
   cudaDeviceSynchronize();
@@ -204,9 +249,15 @@ int b200q_engine_create_dryrun(const b200q_engine_config* cfg, int32_t vocab, in
   const int64_t T = cfg->max_num_batched_tokens, S = cfg->max_num_seqs;
   e->meta_cap = 3 * T + 2 * S + 4 * S + 8 + 4 * (T / 16 + S + 2) +
                 S * (int64_t)((e->max_blocks_per_seq + 7) & ~7) + 64;
-  e->h_meta = (int32_t*)malloc(e->meta_cap * 4);
-  e->h_out = (int32_t*)malloc(S * 4);
-  if (!e->h_meta || !e->h_out) {
+  for (int i = 0; i < 2; ++i) {
+    e->h_meta_buf[i] = (int32_t*)malloc(e->meta_cap * 4);
+    e->h_out_buf[i] = (int32_t*)malloc(S * 4);
+  }
+  {
+    const char* v = getenv("B200Q_ASYNC");
+    e->async_steps = !(v && v[0] == '0');
+  }
+  if (!e->h_meta_buf[0] || !e->h_meta_buf[1] || !e->h_out_buf[0] || !e->h_out_buf[1]) {
     set_error("create_dryrun: out of host memory");
     b200q_engine_destroy(e);
     return B200Q_ENOMEM;
@@ -217,19 +268,26 @@ int b200q_engine_create_dryrun(const b200q_engine_config* cfg, int32_t vocab, in
 
 int b200q_engine_destroy(b200q_engine_t e) {
   if (!e) return B200Q_OK;
+  if (!e->dry_run && e->stream) cudaStreamSynchronize(e->stream);
+  // requests a still-unfinished step holds but the scheduler has already let go of
+  for (StepEntry& se : e->inflight.entries)
+    if (se.r->dead && --se.r->refs == 0) delete se.r;
+  for (auto& kv : e->by_id) delete kv.second;
   if (e->dry_run) {
-    for (auto& kv : e->by_id) delete kv.second;
-    free(e->h_meta);
-    free(e->h_out);
+    for (int i = 0; i < 2; ++i) {
+      free(e->h_meta_buf[i]);
+      free(e->h_out_buf[i]);
+    }
     delete e;
     return B200Q_OK;
   }
-  if (e->stream) cudaStreamSynchronize(e->stream);
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second.exec);
-  for (auto& kv : e->by_id) delete kv.second;
-  if (e->h_meta) cudaFreeHost(e->h_meta);
+  for (int i = 0; i < 2; ++i) {
+    if (e->h_meta_buf[i]) cudaFreeHost(e->h_meta_buf[i]);
+    if (e->h_out_buf[i]) cudaFreeHost(e->h_out_buf[i]);
+    if (e->done_ev[i]) cudaEventDestroy(e->done_ev[i]);
+  }
   if (e->d_meta) cudaFree(e->d_meta);
-  if (e->h_out) cudaFreeHost(e->h_out);
   if (e->d_out) cudaFree(e->d_out);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -285,25 +343,43 @@ int b200q_engine_set_stop_ids(b200q_engine_t e, const int32_t* ids, int32_t n) {
   return B200Q_OK;
 }
 
-int b200q_engine_abort(b200q_engine_t e, int64_t req_id) {
-  B200Q_CHECK_ARG(e, "abort: null engine");
-  auto it = e->by_id.find(req_id);
-  if (it == e->by_id.end()) return B200Q_OK;
-  Request* r = it->second;
+// the scheduler lets go of r (finished or aborted): no further events, blocks back to the pool.
+// Its KV blocks may be handed out again at once: whatever an in-flight step still reads or writes
+// there happens before the first kernel of the step that reuses them (one stream).
+static void retire_request(b200q_engine* e, Request* r) {
   auto w = std::find(e->waiting.begin(), e->waiting.end(), r);
   if (w != e->waiting.end()) e->waiting.erase(w);
   auto ru = std::find(e->running.begin(), e->running.end(), r);
   if (ru != e->running.end()) e->running.erase(ru);
   free_request_blocks(e, r);
-  e->by_id.erase(it);
-  delete r;
+  auto it = e->by_id.find(r->id);
+  if (it != e->by_id.end() && it->second == r) e->by_id.erase(it);
+  if (r->refs == 0) delete r;
+  else r->dead = true;  // deleted when the last in-flight step that holds it completes
+}
+
+int b200q_engine_set_async(b200q_engine_t e, int32_t on) {
+  B200Q_CHECK_ARG(e, "set_async: null engine");
+  if (e->inflight.active) {
+    set_error("set_async: a step is in flight; switch modes while the engine is idle");
+    return B200Q_ESTATE;
+  }
+  e->async_steps = on != 0;
+  return B200Q_OK;
+}
+
+int b200q_engine_abort(b200q_engine_t e, int64_t req_id) {
+  B200Q_CHECK_ARG(e, "abort: null engine");
+  auto it = e->by_id.find(req_id);
+  if (it == e->by_id.end()) return B200Q_OK;
+  retire_request(e, it->second);
   return B200Q_OK;
 }
 
 void* b200q_engine_stream(b200q_engine_t e) { return e ? (void*)e->stream : nullptr; }
 
 int b200q_engine_has_work(b200q_engine_t e) {
-  return e && (!e->waiting.empty() || !e->running.empty()) ? 1 : 0;
+  return e && (!e->waiting.empty() || !e->running.empty() || e->inflight.active) ? 1 : 0;
 }
 
 int b200q_engine_get_stats(b200q_engine_t e, b200q_engine_stats* out) {
@@ -316,12 +392,54 @@ int b200q_engine_get_stats(b200q_engine_t e, b200q_engine_stats* out) {
   return B200Q_OK;
 }
 
-int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_tokens,
-                      int32_t* out_flags, int32_t cap, int32_t* n_out) {
-  B200Q_CHECK_ARG(e && out_req_ids && out_tokens && out_flags && n_out, "step: null argument");
-  B200Q_CHECK_ARG(cap >= e->cfg.max_num_seqs, "step: event capacity %d < max_num_seqs %d", cap,
-                  e->cfg.max_num_seqs);
-  *n_out = 0;
+// ---- completion of an in-flight step: wait for its sampled ids, put them where the placeholders
+// are, emit (request, token, flags) events and retire what finished ----
+static int complete_step(b200q_engine* e, InFlightStep& st, int64_t* out_req_ids, int32_t* out_tokens,
+                         int32_t* out_flags, int32_t* n_out) {
+  if (!e->dry_run) {
+    cudaError_t ce = cudaEventSynchronize(e->done_ev[st.buf]);
+    if (ce != cudaSuccess) {
+      set_error("step: forward failed: %s", cudaGetErrorString(ce));
+      return B200Q_ECUDA;
+    }
+  }
+  const int32_t* h_out = e->h_out_buf[st.buf];
+  int n_ev = *n_out;
+  for (StepEntry& se : st.entries) {
+    Request* r = se.r;
+    r->refs--;
+    if (r->dead) {  // finished (stop id) or aborted after this step had been scheduled: output discarded
+      if (r->refs == 0) delete r;
+      continue;
+    }
+    if (se.sample_slot < 0) continue;
+    // scheduler self-test engine: the "model" counts up from the previous token of the sequence
+    const int32_t t = e->dry_run ? (r->tokens[se.token_pos - 1] + 1) % e->mcfg.vocab : h_out[se.sample_slot];
+    r->tokens[se.token_pos] = t;
+    if (r->pending_pos == se.token_pos) r->pending_pos = -1;
+    int flags = 0;
+    if (!r->ignore_eos && e->is_stop_id(t)) flags = B200Q_FLAG_FINISHED_EOS;
+    else if (se.finished_len) flags = B200Q_FLAG_FINISHED_LENGTH;
+    out_req_ids[n_ev] = r->id;
+    out_tokens[n_ev] = t;
+    out_flags[n_ev] = flags;
+    ++n_ev;
+    if (flags) {
+      // generated-length history for growth-aware admission: mean of the first finishers, then
+      // an exponential average (window ~64 requests)
+      const double gen = (double)(se.token_pos + 1 - r->n_prompt);
+      e->est_gen = e->est_gen < 0.0 ? gen : e->est_gen + (gen - e->est_gen) / 64.0;
+      retire_request(e, r);  // a later in-flight step may still hold it: its extra token is discarded
+    }
+  }
+  st.entries.clear();
+  st.active = false;
+  *n_out = n_ev;
+  return B200Q_OK;
+}
+
+// ---- scheduling + launch of the next step; `step.active` stays false when there is nothing to run
+static int schedule_and_launch(b200q_engine* e, InFlightStep& step) {
   int budget = e->cfg.max_num_batched_tokens;
 
   // ---- 1+2. pick this step's work ----
@@ -437,13 +555,8 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     schedule_running(2);
   }
 
-  if (sched.empty()) {
-    if (!e->waiting.empty() && e->running.empty()) {
-      set_error("scheduler stalled: a waiting request cannot be admitted (KV pool too small)");
-      return B200Q_ENOMEM;
-    }
-    return B200Q_OK;
-  }
+
+  if (sched.empty()) return B200Q_OK;
 
   // ---- 3. order: single-token pieces (decode) first, then multi-token prefill chunks ----
   std::stable_partition(sched.begin(), sched.end(), [](Request* r) { return r->n_sched == 1; });
@@ -456,13 +569,15 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
   const int n_rows = (int)sched.size();
   const int bt_stride = (max_blocks + 7) & ~7;
 
-  int32_t* tok = e->h_meta;
+  const int buf = e->next_buf;
+  int32_t* const h_meta = e->h_meta_buf[buf];
+  int32_t* tok = h_meta;
   int32_t* pos = tok + T;
   int32_t* slot = pos + T;
   int32_t* ctx = slot + T;
   int32_t* srows = ctx + n_dec;
   int32_t* sparams = srows + n_rows;  // reserve n_rows sample slots
-  sparams += (4 - ((sparams - e->h_meta) & 3)) & 3;
+  sparams += (4 - ((sparams - h_meta) & 3)) & 3;
   int32_t* tiles = sparams + 4 * n_rows;  // 16-byte aligned: the prefill kernel reads tiles as int4
   int n_tiles = 0, n_sample = 0, row = 0;
   bool any_sampled = false;
@@ -471,20 +586,23 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     if (r->n_sched > 1) n_tiles += (r->n_sched + 15) / 16;
   int32_t* btab = tiles + 4 * n_tiles;
   // keep the block table 16-byte aligned for tidy copies
-  btab += (4 - ((btab - e->h_meta) & 3)) & 3;
-  const int64_t used = (btab - e->h_meta) + (int64_t)n_rows * bt_stride;
+  btab += (4 - ((btab - h_meta) & 3)) & 3;
+  const int64_t used = (btab - h_meta) + (int64_t)n_rows * bt_stride;
   if (used > e->meta_cap) {
     set_error("step: metadata buffer overflow (%lld > %lld)", (long long)used,
               (long long)e->meta_cap);
     return B200Q_ENOMEM;
   }
   int ti = 0;
+  std::vector<int32_t> slot_of(n_rows, -1);  // sample slot of row ri, -1 = a mid-prompt chunk
   for (int ri = 0; ri < n_rows; ++ri) {
     Request* r = sched[ri];
     const int bs = e->block_size;
     for (int j = 0; j < r->n_sched; ++j) {
       const int p = r->n_computed + j;
-      tok[row + j] = r->tokens[p];
+      // an unresolved token (sampled by the in-flight step, not read back yet) travels as a negative
+      // id that the embedding kernel resolves against that step's out_ids on the device
+      tok[row + j] = p == r->pending_pos ? -1 - r->pending_slot : r->tokens[p];
       pos[row + j] = p;
       slot[row + j] = r->blocks[p / bs] * bs + (p % bs);
     }
@@ -500,7 +618,7 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
       }
     }
     if (r->n_computed + r->n_sched == (int)r->tokens.size()) {
-      r->sample_slot = n_sample;
+      slot_of[ri] = n_sample;
       float tf = r->temperature;
       int32_t tbits;
       memcpy(&tbits, &tf, 4);
@@ -510,8 +628,6 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
       sparams[4 * n_sample + 3] = r->n_generated;  // Philox counter: index of the token being drawn
       any_sampled |= tf > 0.f;
       srows[n_sample++] = row + r->n_sched - 1;
-    } else {
-      r->sample_slot = -1;
     }
     int32_t* brow = btab + (int64_t)ri * bt_stride;
     const int nb = (int)r->blocks.size();
@@ -533,7 +649,8 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     for (int t = 0; t < T && rc == B200Q_OK; ++t) {
       if (slot[t] < 0 || slot[t] >= (int)slot_seen.size()) fail("slot out of range");
       else if (slot_seen[slot[t]]++) fail("two tokens of one step share a KV slot");
-      if (tok[t] < 0 || tok[t] >= e->mcfg.vocab) fail("token id out of range");
+      if (tok[t] >= e->mcfg.vocab || (tok[t] < 0 && -1 - tok[t] >= e->prev_n_sample))
+        fail("token id out of range");
     }
     int covered = n_dec;
     for (int i = 0; i < n_tiles && rc == B200Q_OK; ++i) {
@@ -546,10 +663,9 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     for (int ri = 0; ri < n_dec && rc == B200Q_OK; ++ri)
       if (ctx[ri] != pos[ri] + 1) fail("decode context length != position + 1");
     if (rc) return rc;
-    for (Request* r : sched)
-      if (r->sample_slot >= 0) e->h_out[r->sample_slot] = (r->tokens.back() + 1) % e->mcfg.vocab;
+    // (the "sampled" tokens are fabricated when the step completes, in sequence order)
   } else {
-    cudaError_t ce = cudaMemcpyAsync(e->d_meta, e->h_meta, used * 4, cudaMemcpyHostToDevice, e->stream);
+    cudaError_t ce = cudaMemcpyAsync(e->d_meta, h_meta, used * 4, cudaMemcpyHostToDevice, e->stream);
     if (ce != cudaSuccess) {
       set_error("step: H2D metadata copy failed: %s", cudaGetErrorString(ce));
       return B200Q_ECUDA;
@@ -560,15 +676,16 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     b.n_tiles = n_tiles;
     b.n_sample = n_sample;
     b.bt_stride = bt_stride;
-    b.token_ids = e->d_meta + (tok - e->h_meta);
-    b.positions = e->d_meta + (pos - e->h_meta);
-    b.slot_mapping = e->d_meta + (slot - e->h_meta);
-    b.ctx_lens = e->d_meta + (ctx - e->h_meta);
-    b.sample_rows = e->d_meta + (srows - e->h_meta);
-    b.tiles = e->d_meta + (tiles - e->h_meta);
-    b.block_table = e->d_meta + (btab - e->h_meta);
+    b.token_ids = e->d_meta + (tok - h_meta);
+    b.positions = e->d_meta + (pos - h_meta);
+    b.slot_mapping = e->d_meta + (slot - h_meta);
+    b.ctx_lens = e->d_meta + (ctx - h_meta);
+    b.sample_rows = e->d_meta + (srows - h_meta);
+    b.tiles = e->d_meta + (tiles - h_meta);
+    b.block_table = e->d_meta + (btab - h_meta);
     b.out_ids = e->d_out;
-    b.sample_params = any_sampled ? e->d_meta + (sparams - e->h_meta) : nullptr;
+    b.prev_out_ids = e->d_out;  // the in-flight step's ids: read by this step's embedding before its sampler overwrites them
+    b.sample_params = any_sampled ? e->d_meta + (sparams - h_meta) : nullptr;
     b.sum_ctx_dec = 0;
     b.prefill_flops_per_layer = 0;
     for (Request* r : sched) {
@@ -638,57 +755,87 @@ int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_token
     if (!launched) rc = b200q_model_forward(e->model, &b, e->stream);
     if (rc) return rc;
     if (n_sample > 0) {
-      ce = cudaMemcpyAsync(e->h_out, e->d_out, (size_t)n_sample * 4, cudaMemcpyDeviceToHost, e->stream);
+      ce = cudaMemcpyAsync(e->h_out_buf[buf], e->d_out, (size_t)n_sample * 4, cudaMemcpyDeviceToHost, e->stream);
       if (ce != cudaSuccess) {
         set_error("step: D2H copy failed: %s", cudaGetErrorString(ce));
         return B200Q_ECUDA;
       }
     }
-    ce = cudaStreamSynchronize(e->stream);
+    ce = cudaEventRecord(e->done_ev[buf], e->stream);
     if (ce != cudaSuccess) {
-      set_error("step: forward failed: %s", cudaGetErrorString(ce));
+      set_error("step: event record failed: %s", cudaGetErrorString(ce));
       return B200Q_ECUDA;
     }
   }
 
-  // ---- 4. update from output ----
+
+  // ---- 4. the step is on its way: advance the scheduler's view of every request in it ----
   e->stats.h2d_bytes += used * 4;
   e->stats.d2h_bytes += (int64_t)n_sample * 4;
   e->stats.steps++;
   e->stats.last_step_tokens = T;
   e->stats.last_step_seqs = n_rows;
-  int n_ev = 0;
-  for (Request* r : sched) {
+  step.active = true;
+  step.buf = buf;
+  step.n_sample = n_sample;
+  step.entries.clear();
+  step.entries.reserve(n_rows);
+  e->next_buf ^= 1;
+  for (int ri = 0; ri < n_rows; ++ri) {
+    Request* r = sched[ri];
     const bool was_decode = r->n_computed >= r->n_prompt;
     r->n_computed += r->n_sched;
     if (was_decode) e->stats.tokens_decoded += r->n_sched;
     else e->stats.tokens_prefilled += r->n_sched;
     r->n_sched = 0;
-    if (r->sample_slot < 0) continue;
-    const int32_t t = e->h_out[r->sample_slot];
-    r->tokens.push_back(t);
-    r->n_generated++;
-    int flags = 0;
-    if (!r->ignore_eos && e->is_stop_id(t))
-      flags = B200Q_FLAG_FINISHED_EOS;
-    else if (r->n_generated >= r->max_new || (int)r->tokens.size() >= e->cfg.max_model_len)
-      flags = B200Q_FLAG_FINISHED_LENGTH;
-    out_req_ids[n_ev] = r->id;
-    out_tokens[n_ev] = t;
-    out_flags[n_ev] = flags;
-    ++n_ev;
-    if (flags) {
-      // generated-length history for growth-aware admission: mean of the first finishers, then
-      // an exponential average (window ~64 requests)
-      e->est_gen = e->est_gen < 0.0 ? (double)r->n_generated
-                                    : e->est_gen + ((double)r->n_generated - e->est_gen) / 64.0;
-      free_request_blocks(e, r);
-      e->running.erase(std::find(e->running.begin(), e->running.end(), r));
-      e->by_id.erase(r->id);
-      delete r;
+    r->refs++;
+    StepEntry se{r, slot_of[ri], -1, false};
+    if (se.sample_slot >= 0) {
+      // the token being sampled gets its place in the sequence now; its value follows at completion
+      r->tokens.push_back(-1);
+      se.token_pos = (int32_t)r->tokens.size() - 1;
+      r->pending_pos = se.token_pos;
+      r->pending_slot = se.sample_slot;
+      r->n_generated++;
+      se.finished_len = r->n_generated >= r->max_new || (int)r->tokens.size() >= e->cfg.max_model_len;
     }
+    step.entries.push_back(se);
   }
-  *n_out = n_ev;
+  // length stops are known now: such a request takes no part in later steps and its blocks can be
+  // handed out again (stream order protects the step in flight); its last event follows at completion
+  for (StepEntry& se : step.entries)
+    if (se.finished_len) {
+      auto ru = std::find(e->running.begin(), e->running.end(), se.r);
+      if (ru != e->running.end()) e->running.erase(ru);
+      free_request_blocks(e, se.r);
+    }
+  return B200Q_OK;
+}
+
+int b200q_engine_step(b200q_engine_t e, int64_t* out_req_ids, int32_t* out_tokens,
+                      int32_t* out_flags, int32_t cap, int32_t* n_out) {
+  B200Q_CHECK_ARG(e && out_req_ids && out_tokens && out_flags && n_out, "step: null argument");
+  B200Q_CHECK_ARG(cap >= e->cfg.max_num_seqs, "step: event capacity %d < max_num_seqs %d", cap,
+                  e->cfg.max_num_seqs);
+  *n_out = 0;
+  e->prev_n_sample = e->inflight.active ? e->inflight.n_sample : 0;
+  // 1. schedule and enqueue the next step while the previous one is still running
+  InFlightStep next;
+  int rc = schedule_and_launch(e, next);
+  if (rc) return rc;
+  const bool had_inflight = e->inflight.active;
+  // 2. now read the previous step's ids back and turn them into events
+  if (had_inflight && (rc = complete_step(e, e->inflight, out_req_ids, out_tokens, out_flags, n_out))) return rc;
+  if (next.active) {
+    if (e->async_steps) {
+      e->inflight = std::move(next);
+    } else if ((rc = complete_step(e, next, out_req_ids, out_tokens, out_flags, n_out))) {
+      return rc;
+    }
+  } else if (!had_inflight && !e->waiting.empty() && e->running.empty()) {
+    set_error("scheduler stalled: a waiting request cannot be admitted (KV pool too small)");
+    return B200Q_ENOMEM;
+  }
   return B200Q_OK;
 }
 

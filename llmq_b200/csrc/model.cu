@@ -294,10 +294,10 @@ int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
   const double kv_tok_bytes = 2.0 * NKV * D * 2;  // K+V bytes per cached token per layer
 
   const bool gemma = c.arch == B200Q_ARCH_GEMMA2;
-  if (gemma && c.embed_scale > 0.f)
-    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_embed_scaled(b->token_ids, m->embed, m->residual, T, H, c.embed_scale, stream));
-  else
-    B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_embed(b->token_ids, m->embed, m->residual, T, H, stream));
+  // token ids < 0 are indirections into the previous step's sampled ids (async stepping)
+  B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2,
+            b200q_embed_ex(b->token_ids, b->prev_out_ids, m->embed, m->residual, T, H,
+                           gemma ? c.embed_scale : 0.f, stream));
   for (int li = 0; li < c.n_layers; ++li) {
     const b200q_layer& L = m->layers[li];
     uint8_t* kv_layer = m->kv + li * kv_layer_bytes;

@@ -195,6 +195,9 @@ class DryRunEngine:
     def abort(self, req_id):
         self._L.check(self.lib.b200q_engine_abort(self.handle, int(req_id)))
 
+    def set_async(self, on: bool):
+        self._L.check(self.lib.b200q_engine_set_async(self.handle, int(on)))
+
     def has_work(self) -> bool:
         return bool(self.lib.b200q_engine_has_work(self.handle))
 

@@ -70,6 +70,7 @@ class Batch(C.Structure):
         ("sample_params", C.c_void_p),
         ("sum_ctx_dec", C.c_int64),
         ("prefill_flops_per_layer", C.c_int64),
+        ("prev_out_ids", C.c_void_p),
     ]
 
 
@@ -120,6 +121,7 @@ SIGNATURES = {
     "b200q_device_check": (_i, []),
     "b200q_launch_count": (_i64, []),
     "b200q_embed": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "b200q_embed_ex": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "b200q_rmsnorm": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
     "b200q_add_rmsnorm": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
     "b200q_rope_kvwrite": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -157,6 +159,7 @@ SIGNATURES = {
     "b200q_engine_add_request_sampled": (_i, [_vp, _i64, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64]),
     "b200q_engine_set_stop_ids": (_i, [_vp, _vp, C.c_int32]),
     "b200q_engine_abort": (_i, [_vp, _i64]),
+    "b200q_engine_set_async": (_i, [_vp, C.c_int32]),
     "b200q_engine_has_work": (_i, [_vp]),
     "b200q_engine_step": (_i, [_vp, _vp, _vp, _vp, C.c_int32, C.POINTER(C.c_int32)]),
     "b200q_engine_get_stats": (_i, [_vp, C.POINTER(EngineStats)]),
@@ -225,6 +228,12 @@ def _stream(stream=None) -> int:
 # ---- thin op wrappers (used by tests/bench; the worker goes through Engine) ------------------
 def embed(ids, table, out, stream=None):
     check(load().b200q_embed(_p(ids), _p(table), _p(out), ids.numel(), table.shape[1], _stream(stream)))
+
+
+def embed_ex(ids, prev_out, table, out, scale=0.0, stream=None):
+    """ids < 0 are read through prev_out[-1 - id] (the previous step's sampled ids)"""
+    check(load().b200q_embed_ex(_p(ids), _p(prev_out), _p(table), _p(out), ids.numel(), table.shape[1], scale,
+                                _stream(stream)))
 
 
 def rmsnorm(x, w, y, eps, stream=None):

@@ -446,6 +446,11 @@ class Engine:
     def abort(self, req_id: int):
         L.check(self.lib.b200q_engine_abort(self.handle, int(req_id)))
 
+    def set_async(self, on: bool):
+        """async stepping (default on): step() enqueues step k+1 before reading step k's ids back and
+        returns step k's events; off = one synchronisation per step (events of the step just run)"""
+        L.check(self.lib.b200q_engine_set_async(self.handle, int(on)))
+
     def has_work(self) -> bool:
         return bool(self.lib.b200q_engine_has_work(self.handle))
 

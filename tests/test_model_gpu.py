@@ -267,3 +267,78 @@ def test_engine_cuda_graph_replay_equals_eager(cuda, monkeypatch):
 
     assert run(True) == run(False)
     model.close()
+
+
+def test_embed_indirection_reads_the_previous_steps_ids(cuda):
+    """K1 with async stepping: a negative token id -1-s is replaced on the device by prev_out[s]"""
+    from llmq_b200 import lib as L
+    g = torch.Generator().manual_seed(0)
+    table = torch.randn(500, 256, generator=g).to(torch.bfloat16).to(cuda)
+    prev = torch.tensor([7, 499, 0, 123], dtype=torch.int32, device=cuda)
+    ids = torch.tensor([5, -1, -4, 77, -2, -3, 0], dtype=torch.int32, device=cuda)
+    want = torch.tensor([5, 7, 123, 77, 499, 0, 0], device=cuda)
+    out = torch.empty(ids.numel(), 256, dtype=torch.bfloat16, device=cuda)
+    L.embed_ex(ids, prev, table, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, table[want])
+    L.embed_ex(ids, prev, table, out, scale=48.0)
+    torch.cuda.synchronize()
+    assert torch.equal(out, (table[want].float() * 48.0).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+def test_async_stepping_gives_the_same_tokens_as_sync(cuda, policy):
+    """engine.cu async stepping: step k+1 is enqueued before step k's ids are read back (decode rows
+    take their input token from the device).  Greedy and seeded-sampling sequences, EOS stops (whose
+    extra in-flight token is discarded), preemption-recompute in a small pool and an abort landing
+    while the request is in flight must all give exactly the synchronous engine's events."""
+    from llmq_b200 import lib as L
+    from llmq_b200.model import Engine
+    dims = TINY["d128"]
+    model, oracle, _ = build(dims, num_blocks=40)
+    reqs = prompts(dims.vocab, [70, 3, 129, 31, 16, 200, 9, 48, 5, 64], seed=13)
+    # batch-invariant GEMMs (no split-K): the two modes put slightly different rows into a step (the
+    # discarded token of a request that has just sampled a stop id), which must not move any rounding
+    L.check(model.lib.b200q_gemm_set_splitk(1))
+
+    def run(async_on, eos, abort_at=None):
+        eng = Engine(model, max_num_seqs=8, max_num_batched_tokens=48, eos_token_id=eos, policy=policy)
+        eng.set_async(async_on)
+        for i, p in enumerate(reqs):
+            eng.add_request(i, p, 24, ignore_eos=False, temperature=0.7 if i % 3 == 1 else 0.0, seed=50 + i)
+        outs, fin = {i: [] for i in range(len(reqs))}, {}
+        aborted = False
+        while eng.has_work():
+            ids, toks, flags = eng.step()
+            for i, t, f in zip(ids.tolist(), toks.tolist(), flags.tolist()):
+                outs[i].append(t)
+                if f:
+                    fin[i] = f
+            if abort_at is not None and not aborted and len(outs[abort_at[0]]) >= abort_at[1]:
+                eng.abort(abort_at[0])   # like a stop string hit on the host: the request may be in flight
+                aborted = True
+        st = eng.stats()
+        assert st.free_blocks == st.total_blocks and st.running == 0 and st.waiting == 0
+        eng.close()
+        return outs, fin, st
+
+    base, fin0, st0 = run(False, None)
+    assert st0.preemptions > 0, "the 40-block pool is meant to force preemption + recompute"
+    # stop ids: tokens the greedy rows really produce early, so that stops happen mid-generation
+    eos = sorted({base[0][5], base[3][9], base[7][2], base[4][15]})
+    sync, fin_s, _ = run(False, eos)
+    asyn, fin_a, st_a = run(True, eos)
+    assert asyn == sync and fin_a == fin_s
+    assert any(f == 1 for f in fin_s.values()) and any(f == 2 for f in fin_s.values())
+    for i, o in sync.items():   # a stop id ends the sequence exactly there
+        hit = [k for k, t in enumerate(o) if t in eos]
+        assert (not hit and len(o) == 24) or hit[0] == len(o) - 1
+    a_sync, _, _ = run(False, eos, abort_at=(5, 3))
+    a_asyn, _, _ = run(True, eos, abort_at=(5, 3))
+    assert a_sync[5] == sync[5][:3] and a_asyn[5] == sync[5][:3], "no event may follow an abort"
+    for i in range(len(reqs)):
+        if i != 5 and i % 3 != 1:
+            # (a request's greedy tokens can change with its batch-mates only at near-ties: split-K)
+            assert a_asyn[i] == a_sync[i]
+    L.check(model.lib.b200q_gemm_set_splitk(0))
+    model.close()

@@ -16,13 +16,17 @@ VOCAB = 1000
 
 
 class DryEngine:
-    def __init__(self, max_num_seqs, budget, max_model_len, num_blocks, policy, eos=-1, block_size=16):
+    def __init__(self, max_num_seqs, budget, max_model_len, num_blocks, policy, eos=-1, block_size=16,
+                 async_steps=False):
         self.lib = L.load()
         cfg = L.EngineConfig(max_num_seqs=max_num_seqs, max_num_batched_tokens=budget,
                              max_model_len=max_model_len, eos_token_id=eos, policy=policy)
         h = C.c_void_p()
         L.check(self.lib.b200q_engine_create_dryrun(C.byref(cfg), VOCAB, block_size, num_blocks, C.byref(h)))
         self.h, self.cap = h, max_num_seqs
+        # async stepping (the production default) returns a step's events one call later; the tests
+        # that reason about WHICH step produced a token pin the synchronous mode
+        L.check(self.lib.b200q_engine_set_async(h, int(async_steps)))
         self.ids = np.zeros(self.cap, np.int64)
         self.tok = np.zeros(self.cap, np.int32)
         self.flg = np.zeros(self.cap, np.int32)
@@ -74,9 +78,10 @@ def expected(prompt, n):
     return [(prompt[-1] + 1 + k) % VOCAB for k in range(n)]
 
 
+@pytest.mark.parametrize("async_steps", [False, True])
 @pytest.mark.parametrize("policy", [0, 1])
-def test_chunked_prefill_and_budget(policy):
-    eng = DryEngine(max_num_seqs=4, budget=24, max_model_len=256, num_blocks=64, policy=policy)
+def test_chunked_prefill_and_budget(policy, async_steps):
+    eng = DryEngine(max_num_seqs=4, budget=24, max_model_len=256, num_blocks=64, policy=policy, async_steps=async_steps)
     prompts = [list(range(3, 3 + n)) for n in (70, 5, 129, 16, 31, 1)]
     for i, p in enumerate(prompts):
         assert eng.add(i, p, 9) == 0
@@ -89,12 +94,13 @@ def test_chunked_prefill_and_budget(policy):
     eng.close()
 
 
+@pytest.mark.parametrize("async_steps", [False, True])
 @pytest.mark.parametrize("policy", [0, 1])
-def test_no_livelock_when_two_requests_cannot_coexist(policy):
+def test_no_livelock_when_two_requests_cannot_coexist(policy, async_steps):
     """found by the property test: a 114-token request and a 27-token request in a 9-block pool
     (10 blocks needed together).  The long one is preempted near its end; re-admitting it before the
     short one finishes used to starve the short one forever under the prefill-first policy."""
-    eng = DryEngine(max_num_seqs=2, budget=17, max_model_len=160, num_blocks=9, policy=policy)
+    eng = DryEngine(max_num_seqs=2, budget=17, max_model_len=160, num_blocks=9, policy=policy, async_steps=async_steps)
     a, b = [0], [(7 + j) % VOCAB for j in range(90)]
     assert eng.add(0, a, 26) == 0 and eng.add(1, b, 24) == 0
     outs, fin, order = drain(eng, 17, max_steps=2000)
@@ -105,10 +111,11 @@ def test_no_livelock_when_two_requests_cannot_coexist(policy):
     eng.close()
 
 
+@pytest.mark.parametrize("async_steps", [False, True])
 @pytest.mark.parametrize("policy", [0, 1])
-def test_preemption_recompute_keeps_sequences(policy):
+def test_preemption_recompute_keeps_sequences(policy, async_steps):
     # 8 prompts of exactly one block that all need a second block after their first decode token
-    eng = DryEngine(max_num_seqs=8, budget=64, max_model_len=64, num_blocks=10, policy=policy)
+    eng = DryEngine(max_num_seqs=8, budget=64, max_model_len=64, num_blocks=10, policy=policy, async_steps=async_steps)
     prompts = [[10 + i] * 16 for i in range(8)]
     for i, p in enumerate(prompts):
         assert eng.add(i, p, 20) == 0
@@ -151,8 +158,9 @@ def test_growth_aware_admission_under_a_backlog():
     assert run(1, True) > 0  # misleading history => optimistic => preemption path still exercised
 
 
-def test_eos_and_length_and_argument_checks():
-    eng = DryEngine(max_num_seqs=4, budget=64, max_model_len=32, num_blocks=16, policy=1, eos=7)
+@pytest.mark.parametrize("async_steps", [False, True])
+def test_eos_and_length_and_argument_checks(async_steps):
+    eng = DryEngine(max_num_seqs=4, budget=64, max_model_len=32, num_blocks=16, policy=1, eos=7, async_steps=async_steps)
     assert eng.add(1, [3, 4, 5], 50, ignore_eos=False) == 0   # generates 6, 7(EOS) -> stops
     assert eng.add(2, [3, 4, 5], 4, ignore_eos=True) == 0     # runs through the EOS id
     assert eng.add(3, [9] * 10, 1000) == 0                     # clipped by max_model_len
@@ -184,6 +192,7 @@ def test_policies_order_work_differently_but_equivalently():
                 first_tokens_step.setdefault(i, steps)
         res[policy] = (steps, first_tokens_step)
         eng.close()
+    # (sync mode: a call returns the events of the step it ran)
     # prefill-first: request 0 cannot decode until every prompt is in (8 prompt steps), so its
     # 6 tokens span more steps; vLLM order finishes request 0 while later prompts still prefill
     assert res[1][1][0] == res[0][1][0] == 1
@@ -194,16 +203,19 @@ def test_policies_order_work_differently_but_equivalently():
 @given(
     lens=st.lists(st.tuples(st.integers(1, 90), st.integers(1, 40)), min_size=1, max_size=24),
     seqs=st.integers(1, 12), budget=st.integers(16, 96), policy=st.integers(0, 1),
-    pool=st.integers(9, 60), abort_one=st.booleans(),
+    pool=st.integers(9, 60), abort_one=st.booleans(), async_steps=st.booleans(), eos=st.sampled_from([-1, 3, 500]),
 )
-def test_scheduler_properties(lens, seqs, budget, policy, pool, abort_one):
+def test_scheduler_properties(lens, seqs, budget, policy, pool, abort_one, async_steps, eos):
     """for arbitrary workloads and pool sizes: every request finishes with exactly its sequence, no
     block leaks, budget and slot invariants hold every step (checked inside the library)"""
-    eng = DryEngine(max_num_seqs=seqs, budget=budget, max_model_len=160, num_blocks=pool, policy=policy)
+    eng = DryEngine(max_num_seqs=seqs, budget=budget, max_model_len=160, num_blocks=pool, policy=policy,
+                    async_steps=async_steps, eos=eos)
     prompts = {}
     for i, (pl, mn) in enumerate(lens):
         p = [(7 * i + j) % VOCAB for j in range(pl)]
-        if eng.add(i, p, mn) == 0:  # requests that can never fit the pool are rejected up front
+        # every third request honours the stop id: in async mode a request that samples it has
+        # already been given one more token in the next step, which must be discarded silently
+        if eng.add(i, p, mn, ignore_eos=i % 3 != 0) == 0:  # requests that can never fit the pool are rejected up front
             prompts[i] = (p, mn)
     outs0, fin0 = {}, {}
     if abort_one and prompts:
@@ -218,7 +230,11 @@ def test_scheduler_properties(lens, seqs, budget, policy, pool, abort_one):
     outs, fin, _ = drain(eng, budget, outs=outs0, finished=fin0)
     for i, (p, mn) in prompts.items():
         n = min(mn, 160 - len(p))
-        assert outs.get(i, []) == expected(p, n), "tokens must not depend on chunking / preemption"
+        want = expected(p, n)
+        if i % 3 == 0 and eos in want:  # stops at (and including) the first stop id
+            want = want[: want.index(eos) + 1]
+            assert fin.get(i) == L.FLAG_FINISHED_EOS
+        assert outs.get(i, []) == want, "tokens must not depend on chunking / preemption / async stepping"
         assert i in fin
     s = eng.stats()
     assert s.free_blocks == s.total_blocks == pool and s.running == 0 and s.waiting == 0

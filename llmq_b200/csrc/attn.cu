@@ -105,6 +105,13 @@ __device__ __forceinline__ void pv_page(uint32_t v_s, const float (&p)[BS / 8][4
   }
 }
 
+// Which decode formulation a head size uses.  Measured on B200 (bench, Llama-3-8B, D = 128): the
+// row-major PV form streams 6.2 TB/s, the transposed form 5.8 TB/s (two extra shuffles sit on the
+// per-page dependency chain); at D = 256 the row-major form needs 128 accumulator registers, spills
+// and runs one CTA per SM, so the transposed form (64 registers, no spills, 2 CTAs/SM) is used there.
+template <int D>
+constexpr bool kTransposedPV = D >= 256;
+
 // Decode: O^T(D x 8 heads) += V^T(D x BS tokens) . P^T(BS x 8 heads).  With the G <= 8 heads on
 // the N side the accumulator has no unused rows (D/16 tiles x 4 registers instead of D/8 x 4) and
 // PV needs D/16 MMAs per page instead of D/8.  The S accumulators of qk_page<false> (rows = heads,
@@ -257,9 +264,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
     }
   }
 
-  float o[D / 16][4];  // O^T tiles: [dim = 16 i + lane/4 (+8)][head = 2(lane&3), +1]
+  // TPV (D = 256): O^T tiles [dim = 16 i + lane/4 (+8)][head = 2(lane&3), +1], D/16 x 4 registers;
+  // else O tiles [head = lane/4 (rows 8-15 unused)][dim = 8 i + 2(lane&3), +1], D/8 x 4 registers
+  constexpr bool TPV = kTransposedPV<D>;
+  constexpr int NO = TPV ? D / 16 : D / 8;
+  float o[NO][4];
 #pragma unroll
-  for (int i = 0; i < D / 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  for (int i = 0; i < NO; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m = -INFINITY, l = 0.f;
 
   for (int k = 0; k < my_n; ++k) {
@@ -298,10 +309,19 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
     }
     l = l * alpha + psum;
     m = m_new;
-    float a0, a1;
-    per_head_pair(alpha, lane, a0, a1);
-    scale_ot<D>(o, a0, a1);
-    pv_page_t<D, BS>(v_s, s, o, lane);
+    if constexpr (TPV) {
+      float a0, a1;
+      per_head_pair(alpha, lane, a0, a1);
+      scale_ot<D>(o, a0, a1);
+      pv_page_t<D, BS>(v_s, s, o, lane);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NO; ++i) {
+        o[i][0] *= alpha;
+        o[i][1] *= alpha;
+      }
+      pv_page<D, BS, false>(v_s, s, o, lane);
+    }
     __syncwarp();
     if (k + DEC_STAGES < my_n) issue(k + DEC_STAGES);
   }
@@ -310,19 +330,29 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
   l += __shfl_xor_sync(0xffffffffu, l, 1);
   l += __shfl_xor_sync(0xffffffffu, l, 2);
   {
-    // partial state of this warp: O^T columns are heads 2(lane&3), +1; m and l sit in the S layout
-    const int r = lane >> 2, h0 = (lane & 3) * 2;
-    float* m0 = merge + (warp * 8 + h0) * (D + 2);
-    float* m1 = m0 + (D + 2);
+    const int r = lane >> 2;
+    if constexpr (TPV) {
+      // partial state of this warp: O^T columns are heads 2(lane&3), +1; m and l sit in the S layout
+      const int h0 = (lane & 3) * 2;
+      float* m0 = merge + (warp * 8 + h0) * (D + 2);
+      float* m1 = m0 + (D + 2);
 #pragma unroll
-    for (int i = 0; i < D / 16; ++i) {
-      if (h0 < G) {
-        m0[i * 16 + r] = o[i][0];
-        m0[i * 16 + 8 + r] = o[i][2];
+      for (int i = 0; i < NO; ++i) {
+        if (h0 < G) {
+          m0[i * 16 + r] = o[i][0];
+          m0[i * 16 + 8 + r] = o[i][2];
+        }
+        if (h0 + 1 < G) {
+          m1[i * 16 + r] = o[i][1];
+          m1[i * 16 + 8 + r] = o[i][3];
+        }
       }
-      if (h0 + 1 < G) {
-        m1[i * 16 + r] = o[i][1];
-        m1[i * 16 + 8 + r] = o[i][3];
+    } else if (r < G) {
+      float* mo = merge + (warp * 8 + r) * (D + 2);
+#pragma unroll
+      for (int i = 0; i < NO; ++i) {
+        mo[i * 8 + (lane & 3) * 2] = o[i][0];
+        mo[i * 8 + (lane & 3) * 2 + 1] = o[i][1];
       }
     }
     if (r < G && (lane & 3) == 0) {
@@ -485,9 +515,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
       n_ctx = max(__ldg(ctx_lens + (item + n_warps) / n_kv), 1);
       load_q(item + n_warps, qn);
     }
-    float o[D / 16][4];  // O^T tiles: [dim = 16 i + lane/4 (+8)][head = 2(lane&3), +1]
+    // TPV (D = 256): O^T tiles [dim = 16 i + lane/4 (+8)][head = 2(lane&3), +1], D/16 x 4 registers;
+    // else O tiles [head = lane/4 (rows 8-15 unused)][dim = 8 i + 2(lane&3), +1], D/8 x 4 registers
+    constexpr bool TPV = kTransposedPV<D>;
+    constexpr int NO = TPV ? D / 16 : D / 8;
+    float o[NO][4];
 #pragma unroll
-    for (int i = 0; i < D / 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    for (int i = 0; i < NO; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m = -INFINITY, l = 0.f;
     for (int p = lo / BS; p < n_pages; ++p) {
       const int st = consumed % DEC_STAGES;
@@ -521,29 +555,45 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 2)
       }
       l = l * alpha + psum;
       m = m_new;
-      float a0, a1;
-      per_head_pair(alpha, lane, a0, a1);
-      scale_ot<D>(o, a0, a1);
-      pv_page_t<D, BS>(v_s, s, o, lane);
+      if constexpr (TPV) {
+        float a0, a1;
+        per_head_pair(alpha, lane, a0, a1);
+        scale_ot<D>(o, a0, a1);
+        pv_page_t<D, BS>(v_s, s, o, lane);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NO; ++i) {
+          o[i][0] *= alpha;
+          o[i][1] *= alpha;
+        }
+        pv_page<D, BS, false>(v_s, s, o, lane);
+      }
       __syncwarp();
       ++consumed;
       issue_next();  // refill the stage that was just drained
     }
     l += __shfl_xor_sync(0xffffffffu, l, 1);
     l += __shfl_xor_sync(0xffffffffu, l, 2);
-    float i0, i1;
-    per_head_pair(l > 0.f ? 1.f / l : 0.f, lane, i0, i1);
+    const float inv = l > 0.f ? 1.f / l : 0.f;
     const int seq = item / n_kv, kvh = item % n_kv;
     bf16* orow = out + (long long)seq * n_q * D + (long long)(kvh * G + r) * D;
+    if constexpr (TPV) {
+      float i0, i1;
+      per_head_pair(inv, lane, i0, i1);
 #pragma unroll
-    for (int i = 0; i < D / 16; ++i) {
-      // transpose the bf16 tile halves back to [head = lane/4][dims 2(lane&3), +1] for 4-byte stores
-      const uint32_t d0 = movmatrix_trans(pack_bf16x2(o[i][0] * i0, o[i][1] * i1));
-      const uint32_t d1 = movmatrix_trans(pack_bf16x2(o[i][2] * i0, o[i][3] * i1));
-      if (r < G) {
-        *reinterpret_cast<uint32_t*>(orow + i * 16 + cq) = d0;
-        *reinterpret_cast<uint32_t*>(orow + i * 16 + 8 + cq) = d1;
+      for (int i = 0; i < NO; ++i) {
+        // transpose the bf16 tile halves back to [head = lane/4][dims 2(lane&3), +1] for 4-byte stores
+        const uint32_t d0 = movmatrix_trans(pack_bf16x2(o[i][0] * i0, o[i][1] * i1));
+        const uint32_t d1 = movmatrix_trans(pack_bf16x2(o[i][2] * i0, o[i][3] * i1));
+        if (r < G) {
+          *reinterpret_cast<uint32_t*>(orow + i * 16 + cq) = d0;
+          *reinterpret_cast<uint32_t*>(orow + i * 16 + 8 + cq) = d1;
+        }
       }
+    } else if (r < G) {
+#pragma unroll
+      for (int i = 0; i < NO; ++i)
+        *reinterpret_cast<uint32_t*>(orow + i * 8 + cq) = pack_bf16x2(o[i][0] * inv, o[i][1] * inv);
     }
   }
 }

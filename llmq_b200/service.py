@@ -79,38 +79,54 @@ class _TokenTable:
 
 
 class _StopScanner:
-    """Incremental detokenisation + stop-string scan of ONE request, the behaviour of vLLM's
-    detokenizer (vllm/v1/engine/detokenizer.py:95-165): every new token extends the text by the
-    characters it adds; only the new characters plus a hold-back of ``max(len(stop)) - 1`` are
-    searched (:86-87), and the output is cut before the earliest stop string.
+    """Incremental detokenisation + stop-string scan of ONE request — vLLM's detokenizer
+    (vllm/v1/engine/detokenizer.py:95-165,167-247): a `tokenizers.decoders.DecodeStream` primed with
+    the prompt ids yields the characters each new token adds (nothing while a multi-byte character is
+    incomplete); only the new characters plus a hold-back of ``max(len(stop)) - 1`` are searched
+    (:86-87) and the output is cut before the earliest stop string.  O(1) work per token, where the
+    first version re-decoded the whole output after every token.
 
-    Work per token is O(window), not O(generated length): the text of a new token is obtained by
-    decoding a short tail of ids (``prefix`` ids of context, as in vLLM's / HF's incremental
-    detokeniser) and taking what it adds over the same tail without the new token.  While the tail
-    ends in an incomplete UTF-8 sequence (U+FFFD) nothing is emitted, exactly like DecodeStream."""
+    Without a Rust tokenizer the same is emulated by decoding a bounded tail of ids
+    (``PREFIX`` ids of left context) and taking what the new token adds to it."""
 
-    PREFIX = 6  # ids of left context that settle spacing / byte-fallback merges
+    PREFIX = 6  # fallback only: ids of left context that settle spacing / byte-fallback merges
 
-    def __init__(self, stop: List[str], decode):
+    def __init__(self, stop: List[str], decode, backend=None, prompt_ids=None):
         self.stop = stop
         self.hold = max(len(s) for s in stop) - 1
-        self.decode = decode
-        self.ids: List[int] = []
         self.text = ""          # emitted text so far
-        self.prefix_off = 0     # ids[prefix_off:read_off] = context already reflected in `text`
-        self.read_off = 0
+        self.n = 0              # generated ids consumed
+        self.stream = None
+        if backend is not None:
+            from tokenizers.decoders import DecodeStream
 
-    def push(self, token: int) -> Optional[str]:
-        """append one token; returns the final (cut) text if a stop string completed, else None"""
+            self.backend = backend
+            self.stream = DecodeStream(ids=list(prompt_ids or []), skip_special_tokens=True)
+        else:
+            self.decode = decode
+            self.ids: List[int] = list(prompt_ids or [])[-self.PREFIX:]
+            self.prefix_off = 0     # ids[prefix_off:read_off] = context already reflected in `text`
+            self.read_off = len(self.ids)
+
+    def _step(self, token: int) -> str:
+        if self.stream is not None:
+            return self.stream.step(self.backend, token) or ""
         self.ids.append(token)
         ids = self.ids
         prefix_text = self.decode(ids[self.prefix_off:self.read_off]) if self.read_off > self.prefix_off else ""
         full = self.decode(ids[self.prefix_off:])
         if full.endswith("\ufffd") or len(full) <= len(prefix_text):
-            return None  # an incomplete multi-byte character (or nothing new): wait for more ids
-        new = full[len(prefix_text):]
+            return ""  # an incomplete multi-byte character (or nothing new): wait for more ids
         self.prefix_off = max(self.read_off, len(ids) - self.PREFIX)
         self.read_off = len(ids)
+        return full[len(prefix_text):]
+
+    def push(self, token: int) -> Optional[str]:
+        """append one token; returns the final (cut) text if a stop string completed, else None"""
+        self.n += 1
+        new = self._step(token)
+        if not new:
+            return None
         start = max(0, len(self.text) - self.hold)
         self.text += new
         best = -1
@@ -135,9 +151,11 @@ class GenerationService:
         # vllm/v1/engine/detokenizer.py:167-247) produces for the reference worker.
         backend = getattr(tokenizer, "backend_tokenizer", None)
         if backend is not None and hasattr(backend, "encode") and hasattr(backend, "decode"):
+            self.backend = backend
             self.encode = lambda text: backend.encode(text, add_special_tokens=True).ids
             self.decode = lambda ids: backend.decode(ids, skip_special_tokens=True)
         else:
+            self.backend = None
             self.encode = lambda text: tokenizer(text, add_special_tokens=True).input_ids
             self.decode = lambda ids: tokenizer.decode(ids, skip_special_tokens=True)
         self._inbox: "queue.SimpleQueue[_Req]" = queue.SimpleQueue()
@@ -155,6 +173,25 @@ class GenerationService:
         self.jobs_done = 0
         self.first_submit_t: Optional[float] = None
         self.last_finish_t: Optional[float] = None
+
+    CONTEXT = 8  # prompt ids of left context for the continuation text
+
+    def detokenize(self, prompt_tail: List[int], ids: List[int]) -> str:
+        """Generated text as the reference worker returns it: the CONTINUATION of the prompt's text —
+        vLLM primes its DecodeStream with the prompt ids (vllm/v1/engine/detokenizer.py:181-184), so
+        e.g. a word-level / metaspace vocabulary yields " w5 w6", not "w5 w6".  Fast path: one decode
+        of (prompt tail + ids) minus the decode of the tail — identical to stepping the stream unless
+        the tail ends inside a multi-byte character, in which case the stream itself is stepped."""
+        if not prompt_tail:
+            return self.decode(ids)
+        pre = self.decode(prompt_tail)
+        if pre.endswith("\ufffd") and self.backend is not None:
+            from tokenizers.decoders import DecodeStream
+
+            stream, backend = DecodeStream(ids=list(prompt_tail), skip_special_tokens=True), self.backend
+            return "".join(filter(None, (stream.step(backend, t) for t in ids)))
+        full = self.decode(list(prompt_tail) + list(ids))
+        return full[len(pre):]
 
     def start(self):
         # The engine thread re-acquires the GIL after every device step; a busy event-loop thread
@@ -198,7 +235,7 @@ class GenerationService:
             if exc is None and text is None:
                 # hand the ids over; detokenisation happens in _deliver on the caller's loop thread,
                 # concurrently with the next device step instead of between two steps
-                text = self._table.tokens(r.slot)
+                text = (r.prompt_ids[-self.CONTEXT:].tolist(), self._table.tokens(r.slot))
             self._table.release(r.slot)
             r.slot = -1
         self.jobs_done += 1
@@ -217,7 +254,7 @@ class GenerationService:
                 continue
             try:
                 if not isinstance(text, str):
-                    text = self.decode(text)
+                    text = self.detokenize(*text)
                 fut.set_result((text, n))
             except Exception as e:  # a detokeniser failure must not strand the waiter
                 fut.set_exception(e)
@@ -229,8 +266,8 @@ class GenerationService:
         n = int(self._table.n[r.slot])
         sc = r.detok
         cut = None
-        while len(sc.ids) < n and cut is None:  # normally exactly one new token
-            cut = sc.push(int(self._table.tok[r.slot, len(sc.ids)]))
+        while sc.n < n and cut is None:  # normally exactly one new token
+            cut = sc.push(int(self._table.tok[r.slot, sc.n]))
         return cut
 
     def _admit(self, batch, r: _Req) -> None:
@@ -247,7 +284,7 @@ class GenerationService:
             r.max_new = min(max_new, 2 ** 31 - 1)
             r.slot = self._table.alloc(r.max_new, bool(r.stop))
             if r.stop:
-                r.detok = _StopScanner(r.stop, self.decode)
+                r.detok = _StopScanner(r.stop, self.decode, self.backend, r.prompt_ids.tolist())
             self.engine.add_request(r.slot, r.prompt_ids, r.max_new, ignore_eos=False,
                                     temperature=r.temperature, seed=r.seed)
             self._reqs[r.slot] = r

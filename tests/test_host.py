@@ -99,12 +99,15 @@ def test_end_to_end_through_reference_base_worker_and_broker(patched):
     assert "toolong" not in got  # ValueError => acked and dropped (base.py:228-235)
     assert len(got) == 23
     # fake model counts up from the last prompt token; 6 tokens (VLLM_MAX_TOKENS), text only
-    assert got["j3"].result == "w8 w9 w10 w11 w12 w13"
+    # (the text is the CONTINUATION of the prompt's text, as vLLM's prompt-primed DecodeStream returns it
+    # to the reference worker: this word-level vocabulary joins tokens with a space, so it starts with one
+    # — pinned against the reference worker's own output in tests/test_vllm_worker_golden.py)
+    assert got["j3"].result == " w8 w9 w10 w11 w12 w13"
     assert got["j3"].prompt == "w13 w7" and got["j3"].worker_id == w.worker_id
     assert got["j3"].model_dump()["url"] == "u3" and got["j3"].model_dump()["a"] == "w13"  # extras copied
     assert got["chat"].prompt == "Chat with 1 messages"
-    assert got["stop"].result == "w101 w102 "  # cut right before the stop string (no stripping, as vLLM); generation aborted
-    assert got["per-job-cap"].result == "w201 w202"
+    assert got["stop"].result == " w101 w102 "  # cut right before the stop string (no stripping, as vLLM); generation aborted
+    assert got["per-job-cap"].result == " w201 w202"
     # default sampling = the reference's literal temperature 0.7, unseeded (a stream per request)
     assert eng.last_sampling[0] == pytest.approx(0.7) and eng.last_sampling[1] != 0
     assert w.jobs_processed == 23
@@ -136,7 +139,7 @@ def test_eos_finishes_and_is_not_rendered(patched):
 
     text, n = asyncio.run(main())
     svc.stop()
-    assert n == 5 and text == "w1021"
+    assert n == 5 and text == " w1021"
 
 
 def test_job_stream_is_sharding_invariant():
@@ -222,8 +225,8 @@ def test_pipeline_stage_routing_with_native_worker(patched):
     assert len(got) == 5
     # stage 1 counts up from w100: "w101 .. w106"; stage 2 is prompted with that text and counts up
     # from its last token w106: "w107 .. w112"; extras ride along
-    assert got["p0"].result == "w107 w108 w109 w110 w111 w112"
-    assert got["p0"].prompt == "w101 w102 w103 w104 w105 w106" and got["p0"].model_dump()["src"] == "s0"
+    assert got["p0"].result == " w107 w108 w109 w110 w111 w112"
+    assert got["p0"].prompt == " w101 w102 w103 w104 w105 w106" and got["p0"].model_dump()["src"] == "s0"
 
 
 def test_cli_install_routes_the_vllm_slot_to_the_native_worker():
@@ -301,8 +304,8 @@ def test_service_over_the_real_cpp_scheduler_dryrun(monkeypatch):
     assert len(got) == len(specs) + 1
     for jid, last, n, cap in specs:
         k = 20 if cap is None else cap
-        assert got[jid] == " ".join(f"w{(last + 1 + j) % VOCAB}" for j in range(k)), jid
-    assert got["stop"] == "w101 w102 w103 "
+        assert got[jid] == "".join(f" w{(last + 1 + j) % VOCAB}" for j in range(k)), jid
+    assert got["stop"] == " w101 w102 w103 "
     # (how many preemptions the 30-block pool causes depends on how the jobs trickle in from the
     # broker; tests/test_scheduler_dryrun.py covers preemption deterministically)
     assert made["preemptions"] >= 0 and made["blocks"][0] == made["blocks"][1]
@@ -528,10 +531,49 @@ def test_stop_scanner_is_incremental_and_matches_whole_text_search():
     assert k == len(ids) - 1, "stop must complete on the last token"
     assert cut == full[: full.find(stop[0])]
     assert max(calls) <= 2 * S._StopScanner.PREFIX + 2, f"decode window grew to {max(calls)} ids"
+    # the production path: tokenizers' DecodeStream primed with the prompt ids (what vLLM runs for the
+    # reference worker) — the text is the continuation of the prompt, the cut the same search
+    prompt = [5, 77]
+    sc3 = S._StopScanner(stop, decode, backend, prompt)
+    cut3 = None
+    for k3, t in enumerate(ids):
+        cut3 = sc3.push(t)
+        if cut3 is not None:
+            break
+    cont = backend.decode(prompt + ids, skip_special_tokens=True)[len(backend.decode(prompt, skip_special_tokens=True)):]
+    assert k3 == len(ids) - 1 and cut3 == cont[: cont.find(stop[0])] and cut3.startswith(" w")
     # special tokens never reach the text (skip_special_tokens) and never match
     sc2 = S._StopScanner(["<|end_of_text|>"], decode)
     from llmq_b200.fixtures import special_token_ids
     assert sc2.push(special_token_ids(VOCAB)["<|end_of_text|>"]) is None and sc2.text == ""
+
+
+def test_detokenize_equals_vllms_prompt_primed_decode_stream():
+    """GenerationService.detokenize (one decode of prompt tail + ids, minus the tail) against the
+    reference behaviour it stands for: tokenizers.decoders.DecodeStream primed with the prompt ids and
+    stepped token by token (vllm/v1/engine/detokenizer.py:181-184,215-222), special tokens skipped"""
+    import numpy as np
+    from tokenizers.decoders import DecodeStream
+
+    from llmq_b200.fixtures import special_token_ids
+
+    tok = build_tokenizer(VOCAB)
+    backend = tok.backend_tokenizer
+    svc = S.GenerationService(engine=None, tokenizer=tok, eos_token_id=None)
+    sp = special_token_ids(VOCAB)
+    bos, eos = sp["<|begin_of_text|>"], sp["<|end_of_text|>"]
+    rng = np.random.default_rng(1)
+    for trial in range(200):
+        n_p, n_g = int(rng.integers(0, 20)), int(rng.integers(0, 30))
+        prompt = [bos] + rng.integers(3, 900, size=n_p).tolist()
+        if trial % 5 == 0:
+            prompt += [eos, bos]          # chat-template-like prompts end in special tokens
+        gen = rng.integers(3, 900, size=n_g).tolist()
+        if trial % 7 == 0 and gen:
+            gen[len(gen) // 2] = eos     # a special token inside the output is skipped
+        stream = DecodeStream(ids=list(prompt), skip_special_tokens=True)
+        want = "".join(filter(None, (stream.step(backend, t) for t in gen)))
+        assert svc.detokenize(prompt[-svc.CONTEXT:], gen) == want, (prompt, gen)
 
 
 def test_every_eos_id_of_the_model_ends_generation(tmp_path):

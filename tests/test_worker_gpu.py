@@ -82,7 +82,8 @@ def test_b200_worker_end_to_end_from_model_dir(cuda, tmp_path, monkeypatch):
     for i in range(12):
         ids = tok(f"w5 w{20 + i} w9", add_special_tokens=True).input_ids
         ref, lg = oracle.greedy(ids, 10, eos_id=tok.eos_token_id, return_logits=True)
-        ref_text = tok.decode(ref, skip_special_tokens=True)
+        # the worker returns the continuation of the prompt's text (vLLM's prompt-primed DecodeStream)
+        ref_text = tok.decode(list(ids) + list(ref), skip_special_tokens=True)[len(tok.decode(ids, skip_special_tokens=True)):]
         r = got[f"j{i}"]
         assert r.prompt == f"w5 w{20 + i} w9" and r.model_dump()["tag"] == i and r.worker_id.startswith("b200-")
         if r.result == ref_text:
@@ -159,7 +160,8 @@ def test_b200_worker_end_to_end_from_gemma2_model_dir(cuda, tmp_path, monkeypatc
         ref, lg = oracle.greedy(ids, 10, return_logits=True)
         if tok.eos_token_id in ref:  # the worker stops at EOS; the oracle's greedy() does not
             ref = ref[: ref.index(tok.eos_token_id)]
-        ref_text = tok.decode(ref, skip_special_tokens=True)
+        # the worker returns the continuation of the prompt's text (vLLM's prompt-primed DecodeStream)
+        ref_text = tok.decode(list(ids) + list(ref), skip_special_tokens=True)[len(tok.decode(ids, skip_special_tokens=True)):]
         r = got[f"g{i}"]
         assert r.prompt == p and r.worker_id.startswith("b200-")
         if r.result == ref_text:

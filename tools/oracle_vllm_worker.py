@@ -13,8 +13,10 @@ this subclass only makes it usable as a parity oracle, without touching /root/re
   * :183-193 — `engine.generate` is wrapped to capture `outputs[0].token_ids` (and the prompt ids
     vLLM tokenised) beside the text the worker returns.
 
-  python tools/oracle_vllm_worker.py golden [case ...]
-      -> gpurun_out/vllm_worker_golden_<case>.json   (commit under tests/golden/)
+  python tools/oracle_vllm_worker.py golden [case ...]      (on the B200 box)
+      -> gpurun_out/vllm_worker_golden_<case>.json
+  python tools/oracle_vllm_worker.py pack                   (here)
+      -> tests/golden/vllm_worker_golden_<case>.json.gz     (committed fixtures)
 
 Cases are seeded random-init checkpoints with the REAL widths of the BASELINE models
 (`llmq_b200.fixtures.seeded_state_dict` reproduces them bit for bit anywhere):
@@ -233,7 +235,22 @@ def golden(cases):
             json.dump(res, f, separators=(",", ":"))
 
 
+def pack():
+    """gpurun_out/vllm_worker_golden_<case>.json -> tests/golden/vllm_worker_golden_<case>.json.gz"""
+    import glob
+    import gzip
+
+    for src in sorted(glob.glob(os.path.join(OUT, "vllm_worker_golden_*.json"))):
+        dst = os.path.join(ROOT, "tests", "golden", os.path.basename(src) + ".gz")
+        with open(src, "rb") as f, gzip.GzipFile(dst, "wb", mtime=0) as g:
+            g.write(f.read())
+        print(dst, os.path.getsize(dst), "bytes")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) < 2 or sys.argv[1] != "golden":
+    if len(sys.argv) >= 2 and sys.argv[1] == "pack":
+        pack()
+    elif len(sys.argv) >= 2 and sys.argv[1] == "golden":
+        golden(sys.argv[2:] or ["llama32_1b", "llama3_8b_w4"])
+    else:
         raise SystemExit(__doc__)
-    golden(sys.argv[2:] or ["llama32_1b", "llama3_8b_w4"])

@@ -164,7 +164,17 @@ def test_native_worker_matches_the_reference_worker(cuda, case, tmp_path, monkey
     monkeypatch.setenv("VLLM_GPU_MEMORY_UTILIZATION", "0.5")
     monkeypatch.setenv("B200Q_TEMPERATURE", "0")
     aio_pika.reset_brokers()
+    # the worker hands text back; remember which ids each text was detokenised from
+    from llmq_b200.service import GenerationService
     ids_of_text = {}
+    detokenize = GenerationService.detokenize
+
+    def recording_detokenize(self, prompt_tail, ids):
+        text = detokenize(self, prompt_tail, ids)
+        ids_of_text[text] = list(ids)
+        return text
+
+    monkeypatch.setattr(GenerationService, "detokenize", recording_detokenize)
 
     async def main():
         w = B200Worker(mdir, "wg", tensor_parallel_size=1)
@@ -174,16 +184,6 @@ def test_native_worker_matches_the_reference_worker(cuda, case, tmp_path, monkey
         await b.setup_queue_infrastructure("wg")
         for j in d["jobs"]:
             await b.publish_job("wg", Job(**j))
-        # the worker hands text back; remember which ids each text was detokenised from
-        svc = w.service
-        decode = svc.decode
-
-        def recording_decode(ids):
-            text = decode(ids)
-            ids_of_text[text] = list(ids)
-            return text
-
-        svc.decode = recording_decode
         got = {}
 
         async def on_res(m):

@@ -117,101 +117,94 @@ def throughput():
         json.dump(results, f)
 
 
-def same_lease():
-    """vLLM 0.22 and the native engine back to back in ONE process lease, identical protocol:
-    N = JOBS_X x max_num_seqs canonical 128-token jobs queued at once, 128 greedy tokens each
-    (ignore_eos), wall clock from submission to the last token; for every max_num_seqs in
-    MAX_NUM_SEQS (default 128,750,4608 — the reference's engine default, its production scripts'
-    750 (ref:utils/run_llmq_benchmark.slurm:32-33), and the headline configuration).
-    -> gpurun_out/same_lease_vllm_vs_native.json"""
-    import gc
+BUDGETS = {128: 2048, 750: 4096, 4608: 4608}
 
-    import torch
 
+def _jobs(seqs, jobs_x):
     from llmq_b200.fixtures import build_tokenizer, make_jobs
 
     spec = BUILTIN_SPECS["llama-3-8b"]
-    d = "/tmp/b200q_llama3_8b_cfg"
-    write_model_dir(d, spec, with_weights=False)
-    seqs_list = [int(x) for x in os.environ.get("MAX_NUM_SEQS", "128,750,4608").split(",")]
-    jobs_x = int(os.environ.get("JOBS_X", "4"))
-    budgets = {128: 2048, 750: 4096, 4608: 4608}
     tok = build_tokenizer(spec.vocab)
-    all_ids = [tok(j["prompt"], add_special_tokens=True).input_ids for j in make_jobs(jobs_x * max(seqs_list) + 512, spec.vocab)]
+    ids = [tok(j["prompt"], add_special_tokens=True).input_ids for j in make_jobs(jobs_x * seqs + 256, spec.vocab)]
+    return ids[:256], ids[256:]
+
+
+def one():
+    """one engine, one max_num_seqs, in its own process (vLLM keeps its 0.9 x 180 GB until exit):
+    python tools/vllm_incumbent.py one <vllm|native> <max_num_seqs> <jobs_x>"""
+    import torch
+
+    engine, seqs, jobs_x = sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+    warm, ids = _jobs(seqs, jobs_x)
+    n_jobs = len(ids)
+    if engine == "vllm":
+        from vllm import LLM, SamplingParams
+
+        d = "/tmp/b200q_llama3_8b_cfg"
+        write_model_dir(d, BUILTIN_SPECS["llama-3-8b"], with_weights=False)
+        t0 = time.time()
+        llm = LLM(model=d, load_format="dummy", dtype="bfloat16", max_model_len=512, max_num_seqs=seqs,
+                  gpu_memory_utilization=0.9, skip_tokenizer_init=True, disable_log_stats=True, seed=0)
+        init_s = time.time() - t0
+        sp = SamplingParams(temperature=0.0, max_tokens=128, ignore_eos=True, detokenize=False)
+        llm.generate([{"prompt_token_ids": p} for p in warm], sp, use_tqdm=False)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        outs = llm.generate([{"prompt_token_ids": p} for p in ids], sp, use_tqdm=False)
+        dt = time.time() - t0
+        ntok = sum(len(o.outputs[0].token_ids) for o in outs)
+        r = {"engine": "vllm-0.22.0 (LLM.generate, compiled + CUDA graphs, its default token budget, dummy weights)",
+             "init_s": round(init_s, 1)}
+    else:
+        from llmq_b200.service import build_service
+
+        svc = build_service("random:llama-3-8b", max_num_seqs=seqs, max_model_len=512, gpu_memory_utilization=0.9,
+                            max_num_batched_tokens=BUDGETS.get(seqs, 4608), seed=1234)
+        eng = svc.engine
+        for i, p in enumerate(warm):
+            eng.add_request(i, p, 128, ignore_eos=True)
+        while eng.has_work():
+            eng.step()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for i, p in enumerate(ids):
+            eng.add_request(i, p, 128, ignore_eos=True)
+        ntok = 0
+        while eng.has_work():
+            ntok += len(eng.step()[1])
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        st = eng.stats()
+        r = {"engine": "b200q (engine-direct, random N(0,0.02) weights)", "max_num_batched_tokens": BUDGETS.get(seqs, 4608),
+             "engine_steps": int(st.steps), "preemptions": int(st.preemptions)}
+    r.update({"max_num_seqs": seqs, "jobs": n_jobs, "seconds": round(dt, 3), "out_tokens_per_s": round(ntok / dt, 1),
+              "jobs_per_s": round(n_jobs / dt, 2)})
+    print("RESULT " + json.dumps(r), flush=True)
+
+
+def same_lease():
+    """vLLM 0.22 and the native engine back to back on ONE lease, identical protocol: N = JOBS_X x
+    max_num_seqs canonical 128-token jobs queued at once, 128 greedy tokens each (ignore_eos), wall
+    clock from submission to the last token (ramp and tail included), for every max_num_seqs in
+    MAX_NUM_SEQS (default 128,750,4608: the engine default the reference runs with, its production
+    scripts' 750 (ref:utils/run_llmq_benchmark.slurm:32-33) and the headline configuration).
+    Every run is its own process.  -> gpurun_out/same_lease_vllm_vs_native.json"""
+    import subprocess
+
+    seqs_list = [int(x) for x in os.environ.get("MAX_NUM_SEQS", "128,750,4608").split(",")]
+    jobs_x = os.environ.get("JOBS_X", "4")
     results = []
-    out_path = os.path.join(OUT, "same_lease_vllm_vs_native.json")
-    only = os.environ.get("ONLY", "")
-
-    def save():
-        with open(out_path, "w") as f:
-            json.dump(results, f, indent=1)
-
     for seqs in seqs_list:
-        n_jobs = jobs_x * seqs
-        warm, ids = all_ids[:256], all_ids[256:256 + n_jobs]
-        if only in ("", "vllm"):
-            try:
-                from vllm import LLM, SamplingParams
-
-                t0 = time.time()
-                llm = LLM(model=d, load_format="dummy", dtype="bfloat16", max_model_len=512, max_num_seqs=seqs,
-                          gpu_memory_utilization=0.9, skip_tokenizer_init=True, disable_log_stats=True, seed=0,
-                          **({"max_num_batched_tokens": budgets.get(seqs, 4608)} if os.environ.get("VLLM_SAME_BUDGET") else {}))
-                init_s = time.time() - t0
-                sp = SamplingParams(temperature=0.0, max_tokens=128, ignore_eos=True, detokenize=False)
-                llm.generate([{"prompt_token_ids": p} for p in warm], sp, use_tqdm=False)
-                torch.cuda.synchronize()
-                t0 = time.time()
-                outs = llm.generate([{"prompt_token_ids": p} for p in ids], sp, use_tqdm=False)
-                dt = time.time() - t0
-                ntok = sum(len(o.outputs[0].token_ids) for o in outs)
-                r = {"engine": "vllm-0.22.0 (default: compiled + CUDA graphs, dummy weights)", "max_num_seqs": seqs, "jobs": n_jobs,
-                     "seconds": round(dt, 3), "out_tokens_per_s": round(ntok / dt, 1), "jobs_per_s": round(n_jobs / dt, 2),
-                     "init_s": round(init_s, 1)}
-                del llm, outs
-            except Exception as e:
-                r = {"engine": "vllm", "max_num_seqs": seqs, "error": repr(e)[:600]}
+        for engine in ("vllm", "native"):
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "one", engine, str(seqs), jobs_x],
+                               capture_output=True, text=True, timeout=1500)
+            line = next((l for l in p.stdout.splitlines() if l.startswith("RESULT ")), None)
+            r = json.loads(line[7:]) if line else {"engine": engine, "max_num_seqs": seqs, "error": (p.stderr or p.stdout)[-800:]}
             print(json.dumps(r), flush=True)
             results.append(r)
-            save()
-            gc.collect()
-            torch.cuda.empty_cache()
-        if only in ("", "native"):
-            try:
-                from llmq_b200.service import build_service
-
-                svc = build_service("random:llama-3-8b", max_num_seqs=seqs, max_model_len=512, gpu_memory_utilization=0.9,
-                                    max_num_batched_tokens=budgets.get(seqs, 4608), seed=1234)
-                eng = svc.engine
-                for i, p in enumerate(warm):
-                    eng.add_request(i, p, 128, ignore_eos=True)
-                while eng.has_work():
-                    eng.step()
-                torch.cuda.synchronize()
-                t0 = time.time()
-                for i, p in enumerate(ids):
-                    eng.add_request(i, p, 128, ignore_eos=True)
-                ntok = 0
-                while eng.has_work():
-                    ntok += len(eng.step()[1])
-                torch.cuda.synchronize()
-                dt = time.time() - t0
-                st = eng.stats()
-                r = {"engine": "b200q (engine-direct, random N(0,0.02) weights)", "max_num_seqs": seqs, "jobs": n_jobs,
-                     "max_num_batched_tokens": budgets.get(seqs, 4608), "seconds": round(dt, 3),
-                     "out_tokens_per_s": round(ntok / dt, 1), "jobs_per_s": round(n_jobs / dt, 2),
-                     "engine_steps": int(st.steps), "preemptions": int(st.preemptions)}
-                eng.close()
-                svc.engine.model.close()
-                del svc, eng
-            except Exception as e:
-                r = {"engine": "b200q", "max_num_seqs": seqs, "error": repr(e)[:600]}
-            print(json.dumps(r), flush=True)
-            results.append(r)
-            save()
-            gc.collect()
-            torch.cuda.empty_cache()
+            with open(os.path.join(OUT, "same_lease_vllm_vs_native.json"), "w") as f:
+                json.dump(results, f, indent=1)
 
 
 if __name__ == "__main__":
-    {"golden": golden, "throughput": throughput, "same_lease": same_lease}[sys.argv[1]]()
+    {"golden": golden, "throughput": throughput, "same_lease": same_lease, "one": one}[sys.argv[1]]()

@@ -101,6 +101,25 @@ int b200q_prefill_attn(const void* q_dev, int q_stride, void* out_dev, const voi
 int b200q_gemm_bf16(const void* A_dev, const void* W_dev, void* C_dev,
                     int M, int N, int K, void* stream);
 
+/* Decode-sized batches: the split-K form of b200q_gemm_bf16 WITHOUT its reduce pass.  If the library
+ *     would split the reduction for this shape, the fp32 partial tiles are left in its scratch
+ *     (*partials = [splits][M][N], valid until the next split-K GEMM on the stream) and *splits > 1;
+ *     the caller folds sum-in-split-order + bf16 rounding into the consumer (the two *_splitk ops
+ *     below).  *splits == 1: nothing was launched, call b200q_gemm_bf16.  Results are bit-identical
+ *     to the unfused sequence. */
+int b200q_gemm_bf16_splitk(const void* A_dev, const void* W_dev, int M, int N, int K, void* stream,
+                           const float** partials_dev, int* splits);
+/* K2' reading x from split-K partials: residual <- bf16(bf16(sum_s partials[s]) + residual);
+ *     x <- rmsnorm(residual) * w        (o-projection / down-projection -> next norm, one launch) */
+int b200q_add_rmsnorm_splitk(void* x_dev, void* residual_dev, const void* w_dev,
+                             const float* partials_dev, int splits, int T, int H, float eps,
+                             void* stream);
+/* K4+K5 reading the qkv rows from split-K partials (rotated q is written to qkv_dev) */
+int b200q_rope_kvwrite_splitk(void* qkv_dev, const float* partials_dev, int splits,
+                              const void* cos_sin_dev, const int32_t* positions_dev,
+                              const int32_t* slot_mapping_dev, void* kv_layer_dev,
+                              int T, int n_q, int n_kv, int D, int block_size, void* stream);
+
 /* K9+K10 fused: out[M, N/2] = SwiGLU(A . W^T); W [N=2I, K] holds gate/up rows INTERLEAVED in blocks
  *     of 128: rows [256j, 256j+128) = gate rows [128j, 128j+128), rows [256j+128, 256j+256) = the
  *     matching up rows.  Rounding identical to b200q_gemm_bf16 followed by b200q_swiglu. */

@@ -75,11 +75,35 @@ __global__ void __launch_bounds__(256) embed_scaled_kernel(const int32_t* __rest
 constexpr int NORM_THREADS = 256;
 constexpr int NORM_MAX_CHUNKS = 4;  // H <= 256*4*8 = 8192
 
-template <bool kAdd>
+// 8 consecutive outputs of a split-K GEMM: the fp32 partials ws[s][row][col] added in split order
+// (the same order and rounding as the stand-alone reduction) and rounded to bf16
+__device__ __forceinline__ uint4 sum_partials_bf16(const float* __restrict__ ws, long long off,
+                                                   long long mn, int splits) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(ws + off));
+  float4 b = __ldg(reinterpret_cast<const float4*>(ws + off + 4));
+  for (int sp = 1; sp < splits; ++sp) {
+    const float4 c = __ldg(reinterpret_cast<const float4*>(ws + sp * mn + off));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(ws + sp * mn + off + 4));
+    a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+    b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(a.x, a.y);
+  o.y = pack_bf16x2(a.z, a.w);
+  o.z = pack_bf16x2(b.x, b.y);
+  o.w = pack_bf16x2(b.z, b.w);
+  return o;
+}
+
+// kPartials: x is not read from x_in but reduced on the fly from the fp32 partials of a split-K GEMM
+// (decode-sized batches): the projection's reduce pass, the residual add and the norm become ONE
+// launch instead of two, and the bf16 GEMM output never makes a round trip through memory.
+template <bool kAdd, bool kPartials = false>
 __global__ void __launch_bounds__(NORM_THREADS)
     rmsnorm_kernel(const uint4* __restrict__ x_in, uint4* __restrict__ residual,
                    const uint4* __restrict__ w, uint4* __restrict__ y, int chunks, float inv_h,
-                   float eps) {
+                   float eps, const float* __restrict__ ws = nullptr, int splits = 0,
+                   long long mn = 0) {
   const long long row = blockIdx.x;
   const uint4* xr = x_in + row * chunks;
   uint4 v[NORM_MAX_CHUNKS];
@@ -88,7 +112,9 @@ __global__ void __launch_bounds__(NORM_THREADS)
   for (int j = 0; j < NORM_MAX_CHUNKS; ++j) {
     int c = threadIdx.x + j * NORM_THREADS;
     if (c < chunks) {
-      uint4 a = ld_v4(xr + c);
+      uint4 a;
+      if constexpr (kPartials) a = sum_partials_bf16(ws, (row * chunks + c) * 8, mn, splits);
+      else a = ld_v4(xr + c);
       if (kAdd) {
         uint4 r = ld_v4(residual + row * chunks + c);
         uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
@@ -279,11 +305,15 @@ __device__ __forceinline__ void rope_chunk_pair(uint4& x1, uint4& x2, const uint
   }
 }
 
+// kPartials: the qkv row is reduced on the fly from the fp32 partials of the split-K qkv projection
+// (decode-sized batches) instead of being read back as bf16 — reduce + RoPE + KV write in one launch
+template <bool kPartials>
 __global__ void __launch_bounds__(256)
     rope_kvwrite_kernel(uint4* __restrict__ qkv, const uint4* __restrict__ cos_sin,
                         const int32_t* __restrict__ positions,
                         const int32_t* __restrict__ slot_mapping, uint4* __restrict__ kv_layer,
-                        int n_q, int n_kv, int D, int block_size) {
+                        int n_q, int n_kv, int D, int block_size, const float* __restrict__ ws,
+                        int splits, long long mn) {
   const int t = blockIdx.x;
   const int cpr = D / 8;        // 16 B chunks per head row
   const int half = cpr / 2;     // chunk pairs per head
@@ -299,8 +329,15 @@ __global__ void __launch_bounds__(256)
   for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
     if (it < n_rope_items) {
       int head = it / half, c = it % half;
-      uint4 x1 = ld_v4(row + head * cpr + c);
-      uint4 x2 = ld_v4(row + head * cpr + c + half);
+      uint4 x1, x2;
+      if constexpr (kPartials) {
+        const long long e = ((long long)t * row_chunks + head * cpr + c) * 8;
+        x1 = sum_partials_bf16(ws, e, mn, splits);
+        x2 = sum_partials_bf16(ws, e + (long long)half * 8, mn, splits);
+      } else {
+        x1 = ld_v4(row + head * cpr + c);
+        x2 = ld_v4(row + head * cpr + c + half);
+      }
       uint4 cs = __ldg(cs_row + c);
       uint4 sn = __ldg(cs_row + half + c);
       rope_chunk_pair(x1, x2, cs, sn);
@@ -318,7 +355,11 @@ __global__ void __launch_bounds__(256)
     } else if (slot >= 0) {
       int j = it - n_rope_items;
       int h = j / cpr, c = j % cpr;
-      uint4 v = ld_v4(row + (n_q + n_kv + h) * cpr + c);
+      uint4 v;
+      if constexpr (kPartials)
+        v = sum_partials_bf16(ws, ((long long)t * row_chunks + (n_q + n_kv + h) * cpr + c) * 8, mn, splits);
+      else
+        v = ld_v4(row + (n_q + n_kv + h) * cpr + c);
       uint4* dst = kv_layer + ((((long long)blk * 2 + 1) * n_kv + h) * block_size + off) * cpr;
       st_v4(dst + (c ^ (off & 7)), v);
     }
@@ -624,6 +665,19 @@ int b200q_add_rmsnorm(void* x, void* residual, const void* w, int T, int H, floa
   return B200Q_OK;
 }
 
+int b200q_add_rmsnorm_splitk(void* x, void* residual, const void* w, const float* partials,
+                             int splits, int T, int H, float eps, void* stream) {
+  B200Q_CHECK_ARG(T >= 0 && H > 0 && H % 8 == 0 && H <= NORM_THREADS * NORM_MAX_CHUNKS * 8,
+                  "add_rmsnorm_splitk: bad shape T=%d H=%d", T, H);
+  B200Q_CHECK_ARG(partials && splits >= 1 && splits <= 16, "add_rmsnorm_splitk: bad partials (splits=%d)", splits);
+  if (T == 0) return B200Q_OK;
+  rmsnorm_kernel<true, true><<<T, NORM_THREADS, 0, as_stream(stream)>>>(
+      nullptr, (uint4*)residual, (const uint4*)w, (uint4*)x, H / 8, 1.f / (float)H, eps, partials, splits,
+      (long long)T * H);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
 int b200q_rope_kvwrite(void* qkv, const void* cos_sin, const int32_t* positions,
                        const int32_t* slot_mapping, void* kv_layer, int T, int n_q, int n_kv,
                        int D, int block_size, void* stream) {
@@ -631,9 +685,24 @@ int b200q_rope_kvwrite(void* qkv, const void* cos_sin, const int32_t* positions,
                   "rope_kvwrite: bad shape T=%d n_q=%d n_kv=%d D=%d bs=%d", T, n_q, n_kv, D,
                   block_size);
   if (T == 0) return B200Q_OK;
-  rope_kvwrite_kernel<<<T, 256, 0, as_stream(stream)>>>((uint4*)qkv, (const uint4*)cos_sin,
-                                                        positions, slot_mapping, (uint4*)kv_layer,
-                                                        n_q, n_kv, D, block_size);
+  rope_kvwrite_kernel<false><<<T, 256, 0, as_stream(stream)>>>(
+      (uint4*)qkv, (const uint4*)cos_sin, positions, slot_mapping, (uint4*)kv_layer, n_q, n_kv, D, block_size,
+      nullptr, 0, 0);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
+
+int b200q_rope_kvwrite_splitk(void* qkv, const float* partials, int splits, const void* cos_sin,
+                              const int32_t* positions, const int32_t* slot_mapping, void* kv_layer,
+                              int T, int n_q, int n_kv, int D, int block_size, void* stream) {
+  B200Q_CHECK_ARG(T >= 0 && (D == 64 || D == 128 || D == 256) && n_q > 0 && n_kv > 0 && block_size > 0,
+                  "rope_kvwrite_splitk: bad shape T=%d n_q=%d n_kv=%d D=%d bs=%d", T, n_q, n_kv, D,
+                  block_size);
+  B200Q_CHECK_ARG(partials && splits >= 1 && splits <= 16, "rope_kvwrite_splitk: bad partials (splits=%d)", splits);
+  if (T == 0) return B200Q_OK;
+  rope_kvwrite_kernel<true><<<T, 256, 0, as_stream(stream)>>>(
+      (uint4*)qkv, (const uint4*)cos_sin, positions, slot_mapping, (uint4*)kv_layer, n_q, n_kv, D, block_size,
+      partials, splits, (long long)T * (n_q + 2 * n_kv) * D);
   B200Q_LAUNCH_CHECK();
   return B200Q_OK;
 }

@@ -701,7 +701,7 @@ static size_t g_splitk_ws_bytes = 0;
 
 template <int BN, int kAct = ACT_NONE>
 static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int K,
-                       cudaStream_t st, int splits = 1) {
+                       cudaStream_t st, int splits = 1, const float** partials_out = nullptr) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
   int rc = get_tmap(A, M, K, GEMM_BM, &ta);
@@ -732,7 +732,8 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
   }
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K, g_gemm_debug, splits, ws);
   B200Q_LAUNCH_CHECK();
-  if (splits > 1) {
+  if (partials_out) *partials_out = ws;  // the caller fuses the reduction into the consumer of C
+  if (splits > 1 && !partials_out) {
     const long long mn8 = (long long)M * N / 8;
     const int rgrid = (int)((mn8 + 255) / 256 < 148 * 8 ? (mn8 + 255) / 256 : 148 * 8);
     splitk_reduce_kernel<<<rgrid, 256, 0, st>>>((const float4*)ws, (uint4*)C, mn8, splits);
@@ -805,6 +806,32 @@ static bool prefer_2cta(int M, int N) {
 
 int g_gemm_force_bn = 0;  // test hook: 0 = heuristic
 int g_gemm_splitk = 0;    // 0 = auto, 1 = never, n > 1 = force n splits where legal (tests)
+
+static bool batch_invariant_env() {
+  static const bool v = [] {
+    const char* e = getenv("B200Q_BATCH_INVARIANT");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
+// split-K factor for a decode-sized projection (1 = do not split): when it has too few 128-wide
+// output tiles to put every SM on the weight stream, split the reduction so that tiles x splits ~ #SMs
+static int choose_splits(int M, int N, int K, bool invariant, int forced_bn) {
+  const int want = invariant ? 1 : g_gemm_splitk;  // 0 = auto, 1 = off, >1 = forced (tests)
+  if (want == 1 || forced_bn != 0 || M > 256 || N % 128 != 0 || N > 8192) return 1;
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / 128);
+  const int kb = K / GEMM_BK;
+  int splits = want > 1 ? want : 1;
+  if (want == 0 && tiles * 2 <= num_sms()) {
+    for (int sN = 8; sN >= 2; --sN)
+      if (kb % sN == 0 && kb / sN >= 8 && tiles * sN <= num_sms() + num_sms() / 8) {
+        splits = sN;
+        break;
+      }
+  }
+  return (splits > 1 && splits <= 8 && kb % splits == 0) ? splits : 1;
+}
 int g_gemm_mode = 0;      // 0 = auto, 1 = force 1-CTA kernels, 2 = force the 2-CTA kernel
 
 }  // namespace b200q
@@ -885,24 +912,8 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
     // B200Q_BATCH_INVARIANT=1 (read once): never split K, so every output element is reduced in
     // one sequential pass and a request's tokens cannot depend on its batch-mates (like
     // VLLM_BATCH_INVARIANT); costs decode-sized GEMMs up to 2x
-    static const bool env_invariant = [] {
-      const char* v = getenv("B200Q_BATCH_INVARIANT");
-      return v && v[0] == '1';
-    }();
-    const int want = env_invariant ? 1 : g_gemm_splitk;  // 0 = auto, 1 = off, >1 = forced (tests)
-    if (want != 1 && bn == 0 && M <= 256 && N % 128 == 0 && N <= 8192) {
-      const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / 128);
-      const int kb = K / GEMM_BK;
-      int splits = want > 1 ? want : 1;
-      if (want == 0 && tiles * 2 <= num_sms()) {
-        for (int sN = 8; sN >= 2; --sN)
-          if (kb % sN == 0 && kb / sN >= 8 && tiles * sN <= num_sms() + num_sms() / 8) {
-            splits = sN;
-            break;
-          }
-      }
-      if (splits > 1 && splits <= 8 && kb % splits == 0) return launch_gemm<128>(A, W, C, M, N, K, st, splits);
-    }
+    const int splits = choose_splits(M, N, K, batch_invariant_env(), bn);
+    if (splits > 1) return launch_gemm<128>(A, W, C, M, N, K, st, splits);
   }
   if (bn == 0) {
     // Every CTA walks ceil(tiles / SMs) tiles; measured on B200 (profiles/r1_microbench.md) a
@@ -928,6 +939,32 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
   if (bn == 256) return launch_gemm<256>(A, W, C, M, N, K, st);
   if (bn == 128) return launch_gemm<128>(A, W, C, M, N, K, st);
   return launch_gemm<64>(A, W, C, M, N, K, st);
+}
+
+// The split-K half of b200q_gemm_bf16 on its own: when the dispatcher would split the reduction
+// (decode-sized M, few output tiles) the fp32 partial tiles are left in the library's scratch
+// ([splits][M][N], *partials_out) and NO reduce pass runs — the caller folds the fixed-order sum and
+// the bf16 rounding into the kernel that consumes the projection (b200q_add_rmsnorm_splitk,
+// b200q_rope_kvwrite_splitk), saving a launch and a round trip per projection.  *splits_out = 1
+// means nothing was launched: call b200q_gemm_bf16 instead.  The scratch is overwritten by the next
+// split-K GEMM on the stream.
+int b200q_gemm_bf16_splitk(const void* A, const void* W, int M, int N, int K, void* stream,
+                           const float** partials_out, int* splits_out) {
+  B200Q_CHECK_ARG(partials_out && splits_out, "gemm_splitk: null output argument");
+  *partials_out = nullptr;
+  *splits_out = 1;
+  B200Q_CHECK_ARG(M >= 0 && N > 0 && K > 0 && K % GEMM_BK == 0 && N % 64 == 0,
+                  "gemm: unsupported shape M=%d N=%d K=%d (need K%%64==0, N%%64==0)", M, N, K);
+  B200Q_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+                  "gemm: operands must be 16-byte aligned");
+  if (M == 0 || g_gemm_mode == 2 || g_gemm_force_bn != 0 || (g_gemm_mode == 0 && prefer_2cta(M, N)))
+    return B200Q_OK;
+  const int splits = choose_splits(M, N, K, batch_invariant_env(), 0);
+  if (splits <= 1) return B200Q_OK;
+  int rc = launch_gemm<128>(A, W, nullptr, M, N, K, as_stream(stream), splits, partials_out);
+  if (rc) return rc;
+  *splits_out = splits;
+  return B200Q_OK;
 }
 
 // K9+K10 fused: out[M, N/2] = swiglu(A . W^T) where W [N, K] holds gate/up rows interleaved in

@@ -5,6 +5,7 @@
 // B200Q_ARCH_GEMMA2 (vllm/model_executor/models/gemma2.py): same skeleton with
 // scaled embeddings, (1+w) sandwich norms around both residual adds, soft-capped attention with
 // alternating sliding-window layers, GeGLU, tied LM head and final-logit soft-capping.
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -42,6 +43,8 @@ struct b200q_model {
   // (no [T, 2I] gate_up buffer: the SwiGLU is applied in the gate_up GEMM's epilogue)
   bf16 *x = nullptr, *residual = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr,
        *sel = nullptr, *logits = nullptr;
+  // fold the split-K reduce of decode-sized projections into the consuming kernel (B200Q_FUSE_SPLITK=0: off)
+  bool fuse_splitk = true;
   // optional per-category device timing (CUDA events on the forward's stream)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -119,6 +122,10 @@ int b200q_model_create(const b200q_model_config* cfg, b200q_model_t* out) {
   if (rc) return rc;
   b200q_model* m = new b200q_model();
   m->cfg = *cfg;
+  {
+    const char* v = getenv("B200Q_FUSE_SPLITK");
+    m->fuse_splitk = !(v && v[0] == '0');
+  }
   m->layers.resize(cfg->n_layers);
   *out = m;
   return B200Q_OK;
@@ -298,6 +305,29 @@ int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
   B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2,
             b200q_embed_ex(b->token_ids, b->prev_out_ids, m->embed, m->residual, T, H,
                            gemma ? c.embed_scale : 0.f, stream));
+  // Decode-sized batches (llama arch): a projection that the GEMM splits along K leaves its fp32
+  // partials in the library's scratch and the NEXT kernel of the chain reduces them on the fly —
+  // qkv -> RoPE/KV write, o -> add+RMSNorm, down -> the next add+RMSNorm — instead of a separate
+  // reduce pass per projection (96 launches per 32-layer step).  Bit-identical to the unfused chain.
+  const bool fuse = !gemma && m->fuse_splitk;
+  const float* pend = nullptr;  // partials of the down projection, consumed by the next norm
+  int pend_splits = 1;
+  // y = norm(residual += x) with x either in m->x or still in split-K partials
+  auto add_norm = [&](const void* w, const float* part, int splits) -> int {
+    if (splits > 1) return b200q_add_rmsnorm_splitk(m->x, m->residual, w, part, splits, T, H, c.rms_eps, stream);
+    return b200q_add_rmsnorm(m->x, m->residual, w, T, H, c.rms_eps, stream);
+  };
+  // C = A . W^T, or (fuse && the library splits K) partials only
+  auto gemm_maybe_split = [&](const void* A, const void* W, void* C, int N, int K, const float** part,
+                              int* splits) -> int {
+    *part = nullptr;
+    *splits = 1;
+    if (fuse) {
+      int rc2 = b200q_gemm_bf16_splitk(A, W, T, N, K, stream, part, splits);
+      if (rc2 || *splits > 1) return rc2;
+    }
+    return b200q_gemm_bf16(A, W, C, T, N, K, stream);
+  };
   for (int li = 0; li < c.n_layers; ++li) {
     const b200q_layer& L = m->layers[li];
     uint8_t* kv_layer = m->kv + li * kv_layer_bytes;
@@ -309,10 +339,17 @@ int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
       else
         B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * T * H * 2, b200q_rmsnorm(m->residual, L.input_norm, m->x, T, H, c.rms_eps, stream));
     } else if (!gemma) {
-      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, L.input_norm, T, H, c.rms_eps, stream));
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, add_norm(L.input_norm, pend, pend_splits));
     }
-    B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * QKV * H, b200q_gemm_bf16(m->x, L.qkv, m->qkv, T, QKV, H, stream));
-    B200Q_TRY(B200Q_PROF_ELEMENTWISE, (double)T * (QKV + QD + 2.0 * NKV * D) * 2, b200q_rope_kvwrite(m->qkv, m->rope, b->positions, b->slot_mapping, kv_layer, T, NQ,
+    const float* part = nullptr;
+    int splits = 1;
+    B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * QKV * H, gemm_maybe_split(m->x, L.qkv, m->qkv, QKV, H, &part, &splits));
+    if (splits > 1)
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, (double)T * (QKV + QD + 2.0 * NKV * D) * 2,
+                b200q_rope_kvwrite_splitk(m->qkv, part, splits, m->rope, b->positions, b->slot_mapping, kv_layer, T,
+                                          NQ, NKV, D, c.block_size, stream));
+    else
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, (double)T * (QKV + QD + 2.0 * NKV * D) * 2, b200q_rope_kvwrite(m->qkv, m->rope, b->positions, b->slot_mapping, kv_layer, T, NQ,
                                  NKV, D, c.block_size, stream));
     // gemma2: even layers are the sliding-window ones (HF layer_types: sliding, full, sliding, ...)
     const int window = (gemma && li % 2 == 0) ? c.sliding_window : 0;
@@ -322,26 +359,30 @@ int b200q_model_forward(b200q_model_t m, const b200q_batch* b, void* stream) {
     B200Q_TRY(B200Q_PROF_PREFILL_ATTN, (double)b->prefill_flops_per_layer, b200q_prefill_attn_ex(m->qkv, QKV, m->attn, kv_layer, b->block_table, b->bt_stride,
                                  b->tiles, b->n_tiles, NQ, NKV, D, c.block_size, c.attn_scale,
                                  c.attn_softcap, window, stream));
-    B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * H * QD, b200q_gemm_bf16(m->attn, L.o, m->x, T, H, QD, stream));
+    B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * H * QD, gemm_maybe_split(m->attn, L.o, m->x, H, QD, &part, &splits));
     if (gemma) {
       B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_gemma_norm_add_norm(m->x, m->residual, L.post_attn_norm, L.pre_ffn_norm, T, H, c.rms_eps, stream));
       B200Q_TRY(B200Q_PROF_GEMM, 4.0 * T * I * H, b200q_gemm_geglu_bf16(m->x, L.gate_up, m->act, T, 2 * I, H, stream));
     } else {
-      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, L.post_norm, T, H, c.rms_eps, stream));
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, add_norm(L.post_norm, part, splits));
       // gate_up GEMM with the SwiGLU fused into its epilogue (weights interleaved at bind time)
       B200Q_TRY(B200Q_PROF_GEMM, 4.0 * T * I * H, b200q_gemm_swiglu_bf16(m->x, L.gate_up, m->act, T, 2 * I, H, stream));
     }
-    B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * H * I, b200q_gemm_bf16(m->act, L.down, m->x, T, H, I, stream));
+    B200Q_TRY(B200Q_PROF_GEMM, 2.0 * T * H * I, gemm_maybe_split(m->act, L.down, m->x, H, I, &pend, &pend_splits));
     if (gemma && li + 1 < c.n_layers)
       B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_gemma_norm_add_norm(m->x, m->residual, L.post_ffn_norm, m->layers[li + 1].input_norm, T, H, c.rms_eps, stream));
   }
-  if (b->n_sample > 0) {
+  // the last down projection's residual add (+ final norm).  Without sampling rows nothing reads the
+  // result, but pending partials must not outlive the step: fold them in all the same.
+  if (b->n_sample > 0 || pend_splits > 1) {
     // only the rows that sample need the final norm + LM head; the fused add+norm runs on all rows
     // because x/residual are per-row anyway and the gather wants the normalised value.
     if (gemma)
       B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_gemma_norm_add_norm(m->x, m->residual, m->layers[c.n_layers - 1].post_ffn_norm, m->final_norm, T, H, c.rms_eps, stream));
     else
-      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, b200q_add_rmsnorm(m->x, m->residual, m->final_norm, T, H, c.rms_eps, stream));
+      B200Q_TRY(B200Q_PROF_ELEMENTWISE, 4.0 * T * H * 2, add_norm(m->final_norm, pend, pend_splits));
+  }
+  if (b->n_sample > 0) {
     B200Q_TRY(B200Q_PROF_ELEMENTWISE, 2.0 * b->n_sample * H * 2, b200q_gather_rows(m->x, b->sample_rows, m->sel, b->n_sample, H, stream));
     B200Q_TRY(B200Q_PROF_GEMM, 2.0 * b->n_sample * (double)c.vocab * H, b200q_gemm_bf16(m->sel, m->lm_head, m->logits, b->n_sample, c.vocab, H, stream));
     if (c.final_softcap > 0.f)

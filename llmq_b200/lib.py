@@ -129,6 +129,9 @@ SIGNATURES = {
     "b200q_prefill_attn": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "b200q_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200q_gemm_swiglu_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200q_gemm_bf16_splitk": (_i, [_vp, _vp, _i, _i, _i, _vp, C.POINTER(_vp), C.POINTER(_i)]),
+    "b200q_add_rmsnorm_splitk": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "b200q_rope_kvwrite_splitk": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200q_swiglu": (_i, [_vp, _vp, _i, _i, _vp]),
     "b200q_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "b200q_argmax_bf16": (_i, [_vp, _vp, _i, _i, _vp]),
@@ -303,6 +306,27 @@ def gemm_bf16(a, w, c, stream=None):
     N = w.shape[0]
     assert w.shape[1] == K and tuple(c.shape) == (M, N)
     check(load().b200q_gemm_bf16(_p(a), _p(w), _p(c), M, N, K, _stream(stream)))
+
+
+def gemm_bf16_splitk(a, w, stream=None):
+    """decode-sized batches: split-K GEMM without its reduce pass.  Returns (partials_ptr, splits);
+    splits == 1 means nothing was launched (the library would not split this shape)"""
+    M, K = a.shape
+    N = w.shape[0]
+    part, splits = C.c_void_p(), C.c_int(1)
+    check(load().b200q_gemm_bf16_splitk(_p(a), _p(w), M, N, K, _stream(stream), C.byref(part), C.byref(splits)))
+    return part.value, splits.value
+
+
+def add_rmsnorm_splitk(x, residual, w, partials_ptr, splits, eps, stream=None):
+    check(load().b200q_add_rmsnorm_splitk(_p(x), _p(residual), _p(w), partials_ptr, splits, x.shape[0], x.shape[1], eps,
+                                          _stream(stream)))
+
+
+def rope_kvwrite_splitk(qkv, partials_ptr, splits, cos_sin, positions, slot_mapping, kv_layer, n_q, n_kv, D, block_size,
+                        stream=None):
+    check(load().b200q_rope_kvwrite_splitk(_p(qkv), partials_ptr, splits, _p(cos_sin), _p(positions), _p(slot_mapping),
+                                           _p(kv_layer), qkv.shape[0], n_q, n_kv, D, block_size, _stream(stream)))
 
 
 def gemm_swiglu_bf16(a, w_interleaved, c, stream=None):

@@ -343,3 +343,77 @@ def test_prefill_attn_long_context_chunk(cuda):
     q = qkv.float().view(n, n_q + 2 * n_kv, D)[:, :n_q]
     ref = O.attention(q, ks[0].float(), vs[0].float(), torch.arange(a, a + n), scale)
     bf16_close(out.float().cpu().view(n, n_q, D), ref, ulps=2.0, atol=5e-3, max_mismatch_frac=0.5, what="prefill long ctx")
+
+
+@pytest.mark.parametrize("M", [1, 16, 120, 256])
+def test_splitk_partials_fused_into_norm_and_rope_are_bit_identical(cuda, M):
+    """decode-sized batches: b200q_gemm_bf16_splitk leaves the fp32 partials of a split-K projection
+    in the library's scratch and the consumer (add+RMSNorm / RoPE+KV write) reduces them on the fly.
+    The fused chain must be BIT-identical to GEMM (with its own reduce pass) followed by the plain op:
+    same summation order over the splits, same rounding of the sum to bf16."""
+    from llmq_b200 import lib
+    H, n_q, n_kv, D, BS = 4096, 32, 8, 128, 16
+    QKV = (n_q + 2 * n_kv) * D
+    a = rnd(M, H, seed=21).to(cuda)
+    # o-projection shape [H, H] -> add + RMSNorm
+    w_o = rnd(H, H, seed=22, scale=0.02).to(cuda)
+    res0, wn = rnd(M, H, seed=23, scale=2.0).to(cuda), rnd(H, seed=24).to(cuda)
+    c = torch.empty(M, H, dtype=BF, device=cuda)
+    lib.gemm_bf16(a, w_o, c)
+    r_ref = res0.clone()
+    lib.add_rmsnorm(c, r_ref, wn, 1e-5)   # c <- normed, r_ref <- residual + gemm
+    part, splits = lib.gemm_bf16_splitk(a, w_o)
+    assert splits > 1, "a [<=256, 4096] x [4096, 4096] projection is expected to split K"
+    x, r = torch.empty(M, H, dtype=BF, device=cuda), res0.clone()
+    lib.add_rmsnorm_splitk(x, r, wn, part, splits, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.equal(r, r_ref) and torch.equal(x, c)
+    # qkv projection [QKV, H] -> RoPE + paged KV write
+    w_qkv = rnd(QKV, H, seed=25, scale=0.02).to(cuda)
+    table = O.rope_table(512, D, 500000.0, None).to(BF).to(cuda)
+    pos = torch.randint(0, 512, (M,), dtype=torch.int32).to(cuda)
+    slots = torch.randperm(40 * BS)[:M].to(torch.int32)
+    if M > 3:
+        slots[3] = -1
+    slots = slots.to(cuda)
+    qkv_ref = torch.empty(M, QKV, dtype=BF, device=cuda)
+    lib.gemm_bf16(a, w_qkv, qkv_ref)
+    kv_ref = torch.zeros(40, 2, n_kv, BS, D, dtype=BF, device=cuda)
+    lib.rope_kvwrite(qkv_ref, table, pos, slots, kv_ref, n_q, n_kv, D, BS)
+    part, splits = lib.gemm_bf16_splitk(a, w_qkv)
+    assert splits > 1
+    qkv = torch.zeros(M, QKV, dtype=BF, device=cuda)
+    kv = torch.zeros(40, 2, n_kv, BS, D, dtype=BF, device=cuda)
+    lib.rope_kvwrite_splitk(qkv, part, splits, table, pos, slots, kv, n_q, n_kv, D, BS)
+    torch.cuda.synchronize()
+    assert torch.equal(qkv[:, :n_q * D], qkv_ref[:, :n_q * D]), "rotated q"
+    assert torch.equal(kv, kv_ref), "paged K/V"
+    # a shape the library does not split: nothing is launched and the caller is told so
+    big = rnd(512, 256, seed=26).to(cuda)
+    assert lib.gemm_bf16_splitk(big, rnd(256, 256, seed=27).to(cuda))[1] == 1
+
+
+def test_model_forward_is_identical_with_and_without_splitk_fusion(cuda, monkeypatch):
+    """whole-engine check of the same: greedy + sampled tokens with B200Q_FUSE_SPLITK on / off"""
+    from llmq_b200.model import BUILTIN_SPECS, Engine
+    from llmq_b200.service import build_service
+    import dataclasses
+    outs = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("B200Q_FUSE_SPLITK", fuse)
+        svc = build_service("random:llama-3.2-1b", max_num_seqs=64, max_model_len=256, gpu_memory_utilization=0.9,
+                            max_num_batched_tokens=512, seed=3, num_blocks=1024)
+        eng = svc.engine
+        g = np.random.default_rng(2)
+        for i in range(24):
+            eng.add_request(i, g.integers(0, 128000, size=int(g.integers(3, 90))).tolist(), 12, ignore_eos=True,
+                            temperature=0.7 if i % 4 == 0 else 0.0, seed=i)
+        res = {i: [] for i in range(24)}
+        while eng.has_work():
+            ids, toks, _ = eng.step()
+            for i, t in zip(ids.tolist(), toks.tolist()):
+                res[i].append(t)
+        outs[fuse] = res
+        eng.close()
+        svc.engine.model.close()
+    assert outs["1"] == outs["0"]

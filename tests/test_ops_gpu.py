@@ -368,6 +368,8 @@ def test_splitk_partials_fused_into_norm_and_rope_are_bit_identical(cuda, M):
     lib.add_rmsnorm_splitk(x, r, wn, part, splits, 1e-5)
     torch.cuda.synchronize()
     assert torch.equal(r, r_ref) and torch.equal(x, c)
+    # a shape the library does not split: nothing is launched and the caller is told so
+    assert lib.gemm_bf16_splitk(rnd(512, 256, seed=26).to(cuda), rnd(256, 256, seed=27).to(cuda))[1] == 1
     # qkv projection [QKV, H] -> RoPE + paged KV write
     w_qkv = rnd(QKV, H, seed=25, scale=0.02).to(cuda)
     table = O.rope_table(512, D, 500000.0, None).to(BF).to(cuda)
@@ -381,6 +383,9 @@ def test_splitk_partials_fused_into_norm_and_rope_are_bit_identical(cuda, M):
     kv_ref = torch.zeros(40, 2, n_kv, BS, D, dtype=BF, device=cuda)
     lib.rope_kvwrite(qkv_ref, table, pos, slots, kv_ref, n_q, n_kv, D, BS)
     part, splits = lib.gemm_bf16_splitk(a, w_qkv)
+    if M > 128:  # two m-tiles x 48 n-tiles already occupy most SMs: the library does not split this one
+        assert splits == 1
+        return
     assert splits > 1
     qkv = torch.zeros(M, QKV, dtype=BF, device=cuda)
     kv = torch.zeros(40, 2, n_kv, BS, D, dtype=BF, device=cuda)
@@ -388,9 +393,7 @@ def test_splitk_partials_fused_into_norm_and_rope_are_bit_identical(cuda, M):
     torch.cuda.synchronize()
     assert torch.equal(qkv[:, :n_q * D], qkv_ref[:, :n_q * D]), "rotated q"
     assert torch.equal(kv, kv_ref), "paged K/V"
-    # a shape the library does not split: nothing is launched and the caller is told so
-    big = rnd(512, 256, seed=26).to(cuda)
-    assert lib.gemm_bf16_splitk(big, rnd(256, 256, seed=27).to(cuda))[1] == 1
+
 
 
 def test_model_forward_is_identical_with_and_without_splitk_fusion(cuda, monkeypatch):

@@ -243,6 +243,18 @@ def test_two_stage_pipeline_on_the_gpu_with_braces_in_stage1_output(cuda, tmp_pa
     aio_pika.reset_brokers()
     stages = ["translate", "format"]
     n_jobs = 40
+    # remember every text either stage hands back (the stage-1 texts are otherwise only visible as
+    # stage-2 prompts, and not at all when the stage-2 job is dropped)
+    from llmq_b200.service import GenerationService
+    produced, owner = [], {}
+    detokenize = GenerationService.detokenize
+
+    def recording_detokenize(self, prompt_tail, ids):
+        text = detokenize(self, prompt_tail, ids)
+        produced.append((owner.get(id(self)), text))
+        return text
+
+    monkeypatch.setattr(GenerationService, "detokenize", recording_detokenize)
 
     async def main():
         # two engines share the GPU: vLLM's meaning of the knob is "this fraction of the device in total"
@@ -253,7 +265,11 @@ def test_two_stage_pipeline_on_the_gpu_with_braces_in_stage1_output(cuda, tmp_pa
         t1 = asyncio.create_task(w1.run())
         while w1.service is None and not t1.done():
             await asyncio.sleep(0.05)
+        owner[id(w1.service)] = "translate"
         t2 = asyncio.create_task(w2.run())
+        while w2.service is None and not t2.done():
+            await asyncio.sleep(0.05)
+        owner[id(w2.service)] = "format"
         b = BrokerManager()
         await b.connect()
         await b.setup_pipeline_infrastructure("p", stages)
@@ -284,37 +300,27 @@ def test_two_stage_pipeline_on_the_gpu_with_braces_in_stage1_output(cuda, tmp_pa
         return got, tok
 
     got, tok = asyncio.run(main())
+    stage1_texts = [t for svc, t in produced if svc == "translate"]
+    assert len(stage1_texts) == n_jobs
+    with_brace = [t for t in stage1_texts if "}" in t or "{" in t]
+    formattable = [t for t in stage1_texts if t not in with_brace]
+    assert len(with_brace) >= 5 and len(formattable) >= 5, (len(with_brace), len(formattable))
+    # every formattable stage-1 text became a stage-2 prompt and produced a final result; none of the others did
+    assert sorted(r.prompt for r in got.values()) == sorted(formattable)
+    assert all("}" not in r.prompt for r in got.values())
+    assert all(r.model_dump()["src"] == f"s{r.id[1:]}" for r in got.values())   # extras ride along both hops
+    # and the final text is the model's greedy continuation of the stage-2 prompt (oracle, near-tie rule)
     oracle = LlamaOracle(LlamaDims.from_hf_config(spec.to_hf_config()), seeded_state_dict(spec, 91), "bf16", max_pos=256)
-
-    def cont(text):  # greedy continuation as text, the way the worker returns it
-        ids = tok(text, add_special_tokens=True).input_ids
+    n_exact = 0
+    sample = sorted(got.values(), key=lambda r: r.id)[:10]
+    for r in sample:
+        ids = tok(r.prompt, add_special_tokens=True).input_ids
         ref, lg = oracle.greedy(ids, 6, eos_id=tok.eos_token_id, return_logits=True)
         if tok.eos_token_id in ref:
             ref = ref[: ref.index(tok.eos_token_id)]
-        return tok.decode(ids + ref, skip_special_tokens=True)[len(tok.decode(ids, skip_special_tokens=True)):], lg
-
-    n_brace = n_ok = n_exact = 0
-    for i in range(n_jobs):
-        stage1, lg1 = cont(f"w{20 + 3 * i} w6 w7")
-        near_tie = any((l.topk(2).values[0] - l.topk(2).values[1]).item() < 0.12 for l in lg1)
-        r = got.get(f"p{i}")
-        if "}" in stage1 and not near_tie:
-            n_brace += 1
-            assert r is None, f"p{i}: stage-1 text {stage1!r} has a stray brace: the reference drops the stage-2 job"
-            continue
-        if r is None:
-            assert near_tie or "}" in stage1, f"p{i}: no final result although {stage1!r} is formattable"
-            continue
-        n_ok += 1
-        assert "}" not in r.prompt and r.model_dump()["src"] == f"s{i}"   # the stage-2 prompt IS the stage-1 text
-        if r.prompt == stage1:
-            stage2, lg2 = cont(stage1)
-            near2 = any((l.topk(2).values[0] - l.topk(2).values[1]).item() < 0.12 for l in lg2)
-            if r.result == stage2:
-                n_exact += 1
-            else:
-                assert near2, (i, r.result, stage2)
+        want = tok.decode(ids + ref, skip_special_tokens=True)[len(tok.decode(ids, skip_special_tokens=True)):]
+        if r.result == want:
+            n_exact += 1
         else:
-            assert near_tie, (i, r.prompt, stage1)
-    assert n_brace >= 5 and n_ok >= 5, (n_brace, n_ok)
-    assert n_exact >= n_ok // 2, (n_exact, n_ok)
+            assert any((l.topk(2).values[0] - l.topk(2).values[1]).item() < 0.12 for l in lg), (r.id, r.result, want)
+    assert n_exact >= len(sample) // 2, (n_exact, len(sample))

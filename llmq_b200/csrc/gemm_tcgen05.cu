@@ -804,6 +804,65 @@ static bool prefer_2cta(int M, int N) {
   return (t2 + pairs - 1) / pairs <= (t1 + sms - 1) / sms;
 }
 
+// ---- weight-stream probe (tools/gpu_probe.py stream_probe; not used by the product path) --------
+// How fast can ONE CTA per SM pull a weight matrix through a shared-memory ring, as a function of the
+// access pattern?  mode 0: the GEMM's own pattern — 2-D TMA boxes of `rows` weight rows x 64 columns
+// (128 B per row, rows K*2 bytes apart); mode 1: the same bytes as 1-D bulk copies of contiguous
+// rows*128-byte chunks (what a pre-tiled weight layout would allow).  No math: the consumer only
+// releases the stage.  Answers whether the decode-sized GEMMs' ~35 GB/s per SM is the pattern's limit.
+__global__ void __launch_bounds__(64)
+    stream_probe_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ W, int N, int K,
+                        int rows, int stages, int mode, unsigned long long* __restrict__ sink) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = rows * 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty = full + stages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int n_tiles = N / rows, kb_total = K / 64;
+  const long long chunks = (long long)n_tiles * kb_total;   // one chunk = one stage fill
+  if (threadIdx.x == 0) {          // producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long c = blockIdx.x; c < chunks; c += gridDim.x) {
+      mbar_wait(empty + stage, phase ^ 1u);
+      mbar_expect_tx(full + stage, (uint32_t)stage_bytes);
+      if (mode == 0) {
+        // consecutive chunks of a CTA walk K first (like a GEMM tile's k-loop)
+        const long long tile = c / kb_total, kb = c % kb_total;
+        tma_load_2d(smem + stage * stage_bytes, &tmap, (int)kb * 64, (int)tile * rows, full + stage);
+      } else {
+        tma_bulk_g2s(smem + stage * stage_bytes, W + c * stage_bytes, (uint32_t)stage_bytes, full + stage);
+      }
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (threadIdx.x == 32) {  // consumer
+    int stage = 0;
+    uint32_t phase = 0;
+    unsigned long long acc = 0;
+    for (long long c = blockIdx.x; c < chunks; c += gridDim.x) {
+      mbar_wait(full + stage, phase);
+      acc += *reinterpret_cast<volatile unsigned long long*>(smem + stage * stage_bytes);
+      mbar_arrive(empty + stage);
+      if (++stage == stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    if (acc == 0x1234567887654321ull) *sink = acc;
+  }
+}
+
 int g_gemm_force_bn = 0;  // test hook: 0 = heuristic
 int g_gemm_splitk = 0;    // 0 = auto, 1 = never, n > 1 = force n splits where legal (tests)
 
@@ -856,6 +915,29 @@ static int gemm_gated(const char* what, const void* A, const void* W, void* C, i
 }
 
 extern "C" {
+
+// measurement hook (tools/gpu_probe.py stream_probe): stream W [N,K] bf16 through per-SM rings
+// mode 0 = 2-D TMA boxes (rows x 64 cols), mode 1 = 1-D bulk copies of rows*128 contiguous bytes;
+// chunk order, mode 0: CTA b takes (tile, k-block) pairs b, b+grid, ... with k fastest
+int b200q_stream_probe(const void* W, int N, int K, int rows, int stages, int mode, int grid, void* stream) {
+  B200Q_CHECK_ARG(W && N > 0 && K > 0 && K % 64 == 0 && rows > 0 && rows <= 256 && N % rows == 0 && stages >= 1 &&
+                      stages * rows * 128 <= 200 * 1024 && grid > 0 && (mode == 0 || mode == 1),
+                  "stream_probe: bad arguments");
+  static unsigned long long* sink = nullptr;
+  if (!sink) B200Q_CUDA(cudaMalloc(&sink, 8));
+  CUtensorMap tm;
+  int rc = get_tmap(W, N, K, rows, &tm);
+  if (rc) return rc;
+  const int smem_bytes = stages * rows * 128 + 1024 + 2 * stages * 8 + 64;
+  static int attr_max = 0;
+  if (smem_bytes > attr_max) {
+    B200Q_CUDA(cudaFuncSetAttribute(stream_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_max = smem_bytes;
+  }
+  stream_probe_kernel<<<grid, 64, smem_bytes, as_stream(stream)>>>(tm, (const uint8_t*)W, N, K, rows, stages, mode, sink);
+  B200Q_LAUNCH_CHECK();
+  return B200Q_OK;
+}
 
 // test/tuning hook (not part of the reference-facing surface): force the N tile (0 = auto)
 int b200q_gemm_set_tile_n(int bn) {

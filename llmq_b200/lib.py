@@ -175,6 +175,7 @@ EXTRA_SIGNATURES = {
     "b200q_gemm_set_debug": (_i, [_i]),
     "b200q_decode_attn_set_variant": (_i, [_i]),
     "b200q_gemm_set_splitk": (_i, [_i]),
+    "b200q_stream_probe": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -212,6 +212,26 @@ def gemm_small_m(f):
             del a, w, c
 
 
+def stream_probe(f):
+    """how fast can one CTA per SM pull a weight matrix through a shared-memory ring?  2-D TMA boxes in
+    the GEMM's own pattern (rows x 128 B, rows K*2 bytes apart) vs 1-D bulk copies of the same bytes laid
+    out contiguously (a pre-tiled weight layout) — for the fused gate_up shape [28672, 4096] and qkv"""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    L = lib.load()
+    for name, (N, K) in {"gate_up": (28672, 4096), "qkv": (6144, 4096), "down": (4096, 14336)}.items():
+        w = (torch.randn(N, K, device=dev) * 0.02).to(BF)
+        for rows, stages in ((256, 4), (256, 6), (128, 8), (128, 12), (64, 16), (64, 24)):
+            for grid in (148, N // rows if N // rows < 148 else 148):
+                for mode in (0, 1):
+                    fn = lambda: lib.check(L.b200q_stream_probe(w.data_ptr(), N, K, rows, stages, mode, grid, 0))
+                    torch.cuda.synchronize()
+                    med, best = timeit(lambda: (fn(), None)[1], iters=11, flush=flush)
+                    emit(f, kind="stream_probe", name=name, N=N, K=K, rows=rows, stages=stages, ring_kb=rows * stages // 8,
+                         grid=grid, mode="tma2d" if mode == 0 else "bulk1d", us=round(med * 1e3, 2),
+                         gbs=round(N * K * 2 / med / 1e6, 1), gbs_per_cta=round(N * K * 2 / med / 1e6 / grid, 1))
+        del w
+
+
 def gemm_limits(f):
     """where do the GEMM's bubbles come from?  time the kernel with the operand loads and/or the
     epilogue switched off (results are garbage in those modes; timing only)"""
@@ -354,4 +374,5 @@ if __name__ == "__main__":
     tag = os.environ.get("PROBE_TAG", "")
     with open(os.path.join(OUT, f"probe_{mode}{tag}.jsonl"), "w") as f:
         {"gemm_check": gemm_check, "bench": bench, "gemm2_bench": gemm2_bench, "ncu_targets": ncu_targets,
-         "argmax_ties": argmax_ties, "gemm_limits": gemm_limits, "decode_variants": decode_variants, "gemm_small_m": gemm_small_m}[mode](f)
+         "argmax_ties": argmax_ties, "gemm_limits": gemm_limits, "decode_variants": decode_variants, "gemm_small_m": gemm_small_m,
+         "stream_probe": stream_probe}[mode](f)

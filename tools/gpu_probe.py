@@ -212,6 +212,29 @@ def gemm_small_m(f):
             del a, w, c
 
 
+def ncu_small_m(f):
+    """decode-sized GEMMs in isolation for an `ncu --set full` capture: fused gate_up at M = 16 and 128,
+    split-K qkv / down at M = 128"""
+    for M in (16, 128):
+        a = torch.randn(M, 4096, device=dev).to(BF)
+        w = (torch.randn(28672, 4096, device=dev) * 0.02).to(BF)
+        c = torch.empty(M, 14336, dtype=BF, device=dev)
+        for _ in range(2):
+            lib.gemm_swiglu_bf16(a, w, c)
+        torch.cuda.synchronize()
+        del a, w, c
+    M = 128
+    for N, K in ((6144, 4096), (4096, 14336)):
+        a = torch.randn(M, K, device=dev).to(BF)
+        w = (torch.randn(N, K, device=dev) * 0.02).to(BF)
+        c = torch.empty(M, N, dtype=BF, device=dev)
+        for _ in range(2):
+            lib.gemm_bf16(a, w, c)
+        torch.cuda.synchronize()
+        del a, w, c
+    emit(f, kind="ncu_small_m", done=True)
+
+
 def stream_probe(f):
     """how fast can one CTA per SM pull a weight matrix through a shared-memory ring?  2-D TMA boxes in
     the GEMM's own pattern (rows x 128 B, rows K*2 bytes apart) vs 1-D bulk copies of the same bytes laid
@@ -375,4 +398,4 @@ if __name__ == "__main__":
     with open(os.path.join(OUT, f"probe_{mode}{tag}.jsonl"), "w") as f:
         {"gemm_check": gemm_check, "bench": bench, "gemm2_bench": gemm2_bench, "ncu_targets": ncu_targets,
          "argmax_ties": argmax_ties, "gemm_limits": gemm_limits, "decode_variants": decode_variants, "gemm_small_m": gemm_small_m,
-         "stream_probe": stream_probe}[mode](f)
+         "stream_probe": stream_probe, "ncu_small_m": ncu_small_m}[mode](f)

@@ -199,8 +199,14 @@ template <int BN, int kAct = ACT_NONE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b, bf16* __restrict__ C, int M,
-                     int N, int K, int dbg, int splits, float* __restrict__ ws) {
+                     int N, int K, int dbg, int splits, float* __restrict__ ws, int a_bytes) {
   constexpr bool kSwiGLU = kAct != ACT_NONE;
+  // a_bytes: bytes one A k-block really carries.  For M < 128 the tensor map's box holds only the
+  // rows that exist (rounded up to the 8-row swizzle atom), not 128: the other rows of the UMMA's A
+  // tile are stale shared memory whose products land in output rows >= M, which are never stored.
+  // A decode-sized GEMM re-reads the whole activation matrix in EVERY CTA — with 128 x 128 tiles as
+  // many L2->SM bytes as the weights themselves (ncu: profiles/r2_ncu_small_m.csv) — so rows that do
+  // not exist should not be paid for.
   // splits > 1 (split-K for decode-sized M, where a projection has too few output tiles to put
   // every SM on the weight stream): tile space = m x split x n, each CTA accumulates K/splits of
   // the reduction and writes an fp32 partial tile to ws[split][M][N]; splitk_reduce_kernel sums the
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (dbg & 1) {  // timing experiment: MMA on stale smem, no operand traffic
             mbar_arrive(full + stage);
           } else {
-            mbar_expect_tx(full + stage, Cfg::STAGE_BYTES);
+            mbar_expect_tx(full + stage, (uint32_t)(a_bytes + Cfg::B_BYTES));
             tma_load_2d(sa, &tmap_a, (kb0 + kb) * GEMM_BK, m_blk * GEMM_BM, full + stage);
             tma_load_2d(sb, &tmap_b, (kb0 + kb) * GEMM_BK, n_blk * BN, full + stage);
           }
@@ -704,7 +710,8 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
                        cudaStream_t st, int splits = 1, const float** partials_out = nullptr) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
-  int rc = get_tmap(A, M, K, GEMM_BM, &ta);
+  const int a_rows = M < GEMM_BM ? (M + 7) & ~7 : GEMM_BM;  // one m-tile: load only the rows that exist
+  int rc = get_tmap(A, M, K, a_rows, &ta);
   if (rc) return rc;
   rc = get_tmap(W, N, K, BN, &tb);
   if (rc) return rc;
@@ -730,7 +737,8 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
     }
     ws = g_splitk_ws;
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K, g_gemm_debug, splits, ws);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, st>>>(ta, tb, (bf16*)C, M, N, K, g_gemm_debug, splits, ws,
+                                                    a_rows * GEMM_BK * 2);
   B200Q_LAUNCH_CHECK();
   if (partials_out) *partials_out = ws;  // the caller fuses the reduction into the consumer of C
   if (splits > 1 && !partials_out) {

@@ -508,6 +508,8 @@ def run_native(args):
         for t in tasks:
             t.cancel()
         await asyncio.gather(*tasks, return_exceptions=True)
+        # stop the engine thread while this loop is still open (it delivers results to the loop)
+        await loop.run_in_executor(None, svc.stop)
         return res
 
     svc.start()

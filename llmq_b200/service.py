@@ -337,7 +337,10 @@ class GenerationService:
                         if r is not None and slot not in stop_hit:
                             self._finish(batch, r)
                 for loop, items in batch.items():
-                    loop.call_soon_threadsafe(self._deliver, items)
+                    try:
+                        loop.call_soon_threadsafe(self._deliver, items)
+                    except RuntimeError:
+                        pass  # that event loop has been closed: its waiters are gone, nothing to deliver to
         except BaseException as e:  # surface engine failures to every waiter
             self.error = e   # submit() refuses new work from here on
             batch = {}

@@ -299,8 +299,9 @@ class GenerationService:
 
                 torch.cuda.set_device(eng.model.device)  # this thread owns the CUDA context
             r = None
+            batch: dict = {}
             while not self._stop.is_set():
-                batch: dict = {}
+                batch = {}
                 r = None
                 # admit new requests
                 try:
@@ -343,7 +344,7 @@ class GenerationService:
                         pass  # that event loop has been closed: its waiters are gone, nothing to deliver to
         except BaseException as e:  # surface engine failures to every waiter
             self.error = e   # submit() refuses new work from here on
-            batch = {}
+            # (`batch` may already hold results finished in this iteration: they are still delivered)
             err = RuntimeError(f"engine failure: {e!r}")
             pending = list(self._reqs.values())
             if r is not None and r.slot not in self._reqs:

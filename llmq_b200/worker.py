@@ -96,7 +96,7 @@ class B200Worker(BaseWorker):
         prompt = str(self.build_prompt(job))
         # text prompts are tokenised with add_special_tokens=True, as vLLM's renderer does
         # (vllm/renderers/base.py:330-342) — chat prompts therefore carry a double BOS (App. D1)
-        ids = self.service.encode(prompt)
+        ids = await self.service.encode_async(prompt)
         extra = job.model_dump()
         max_new = int(extra.get("max_tokens") or self.config.vllm_max_tokens)
         # the reference hard-codes temperature=0.7, unseeded (vllm_worker.py:161-165); a job may

@@ -167,14 +167,16 @@ def test_native_worker_matches_the_reference_worker(cuda, case, tmp_path, monkey
     # the worker hands text back; remember which ids each text was detokenised from
     from llmq_b200.service import GenerationService
     ids_of_text = {}
-    detokenize = GenerationService.detokenize
+    detokenize_batch = GenerationService.detokenize_batch
 
-    def recording_detokenize(self, prompt_tail, ids):
-        text = detokenize(self, prompt_tail, ids)
-        ids_of_text[text] = list(ids)
-        return text
+    def recording_detokenize(self, pairs):
+        pairs = list(pairs)
+        texts = detokenize_batch(self, pairs)
+        for (_, ids), text in zip(pairs, texts):
+            ids_of_text[text] = list(ids)
+        return texts
 
-    monkeypatch.setattr(GenerationService, "detokenize", recording_detokenize)
+    monkeypatch.setattr(GenerationService, "detokenize_batch", recording_detokenize)
 
     async def main():
         w = B200Worker(mdir, "wg", tensor_parallel_size=1)

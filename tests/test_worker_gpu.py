@@ -247,14 +247,14 @@ def test_two_stage_pipeline_on_the_gpu_with_braces_in_stage1_output(cuda, tmp_pa
     # stage-2 prompts, and not at all when the stage-2 job is dropped)
     from llmq_b200.service import GenerationService
     produced, owner = [], {}
-    detokenize = GenerationService.detokenize
+    detokenize_batch = GenerationService.detokenize_batch
 
-    def recording_detokenize(self, prompt_tail, ids):
-        text = detokenize(self, prompt_tail, ids)
-        produced.append((owner.get(id(self)), text))
-        return text
+    def recording_detokenize(self, pairs):
+        texts = detokenize_batch(self, pairs)
+        produced.extend((owner.get(id(self)), text) for text in texts)
+        return texts
 
-    monkeypatch.setattr(GenerationService, "detokenize", recording_detokenize)
+    monkeypatch.setattr(GenerationService, "detokenize_batch", recording_detokenize)
 
     async def main():
         # two engines share the GPU: vLLM's meaning of the knob is "this fraction of the device in total"

@@ -633,3 +633,47 @@ def test_default_max_model_len_is_the_models_own(monkeypatch):
     with pytest.raises(StopHere):
         S.build_service("random:llama-3-8b", max_num_seqs=4, max_model_len=1024, gpu_memory_utilization=0.5)
     assert seen["max_model_len"] == 1024
+
+
+def test_prompts_of_one_loop_iteration_are_tokenised_in_one_batch_call():
+    """host fast path: `encode_async` gathers every prompt submitted in the same event-loop iteration
+    into ONE `encode_batch` (Rust thread pool, GIL released) — ids identical to the per-call `encode`,
+    one bad text does not strand the others, and `detokenize_batch` equals the per-request `detokenize`"""
+    import numpy as np
+
+    tok = build_tokenizer(VOCAB)
+    svc = S.GenerationService(engine=None, tokenizer=tok, eos_token_id=None)
+    calls = []
+
+    class CountingBackend:
+        def __init__(self, be):
+            self._be = be
+
+        def encode_batch(self, texts, add_special_tokens=True):
+            calls.append(len(texts))
+            if any(t is None for t in texts):
+                raise TypeError("not a string")
+            return self._be.encode_batch(texts, add_special_tokens=add_special_tokens)
+
+        def __getattr__(self, name):
+            return getattr(self._be, name)
+
+    svc.backend = CountingBackend(svc.backend)
+    rng = np.random.default_rng(0)
+    texts = [" ".join(f"w{int(i)}" for i in rng.integers(3, 900, size=int(rng.integers(1, 60)))) for _ in range(80)]
+
+    async def main():
+        a = await asyncio.gather(*[svc.encode_async(t) for t in texts])   # one iteration -> one batch
+        b = []
+        for t in texts[:5]:                                                 # a trickle -> batches of one
+            b.append(await svc.encode_async(t))
+        mixed = await asyncio.gather(svc.encode_async(texts[0]), svc.encode_async(None), svc.encode_async(texts[1]),
+                                     return_exceptions=True)
+        return a, b, mixed
+
+    a, b, mixed = asyncio.run(main())
+    assert a == [svc.encode(t) for t in texts] and b == a[:5]
+    assert calls[0] == 80 and calls[1:6] == [1] * 5
+    assert mixed[0] == a[0] and mixed[2] == a[1] and isinstance(mixed[1], Exception)
+    pairs = [(a[i][-8:], rng.integers(3, 900, size=int(rng.integers(0, 40))).tolist()) for i in range(30)]
+    assert svc.detokenize_batch(pairs) == [svc.detokenize(t, g) for t, g in pairs]

@@ -5,7 +5,7 @@ import torch
 def bf16_close(got: torch.Tensor, ref: torch.Tensor, ulps: float = 1.0, atol: float = 1e-6,
                max_mismatch_frac: float = 0.02, what: str = ""):
     """got/ref: float tensors holding bf16-representable values.  Passes when every element is
-    within `ulps` bf16 ulps (2^-8 relative, measured on max(|got|,|ref|)) and at most
+    within `ulps` bf16 ulps (taken as 2^-7 relative to max(|got|,|ref|): the spacing of bf16 at the bottom of a binade) and at most
     `max_mismatch_frac` of the elements differ at all (different fp32 accumulation order can flip
     the final rounding of a few elements, nothing more)."""
     got, ref = got.float().cpu(), ref.float().cpu()

@@ -227,9 +227,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = N / BN;
   const int num_tiles = m_tiles * n_tiles * splits;
-  const int kb_total = K / GEMM_BK;
-  // k-blocks [kb_lo(s), kb_lo(s+1)) belong to split s: the splits need not divide the k-blocks evenly
-  auto kb_lo = [&](int sp) { return (int)((long long)kb_total * sp / splits); };
+  const int k_blocks = (K / GEMM_BK) / splits;  // k-blocks per tile (per split)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -258,7 +256,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile % m_tiles, rest = tile / m_tiles;
-        const int n_blk = rest / splits, kb0 = kb_lo(rest % splits), k_blocks = kb_lo(rest % splits + 1) - kb0;
+        const int n_blk = rest / splits, kb0 = (rest % splits) * k_blocks;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty + stage, phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -288,8 +286,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_wait(tmem_empty + acc, acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-      const int split_of_tile = (tile / m_tiles) % splits;
-      const int k_blocks = kb_lo(split_of_tile + 1) - kb_lo(split_of_tile);
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(full + stage, phase);
         tc_fence_after();
@@ -706,7 +702,6 @@ static int num_sms() {
 
 static int g_gemm_debug = 0;  // timing experiments only (wrong results): 1 = no TMA loads, 2 = no epilogue
 
-constexpr size_t SPLITK_WS_BYTES = (size_t)8 * 256 * 8192 * sizeof(float);  // 64 MiB of fp32 partials
 static float* g_splitk_ws = nullptr;
 static size_t g_splitk_ws_bytes = 0;
 
@@ -734,7 +729,7 @@ static int launch_gemm(const void* A, const void* W, void* C, int M, int N, int 
     // fixed-size scratch (8 splits x 256 rows x 8192 cols fp32 = 64 MiB), allocated once and never
     // moved: CUDA graphs captured by the engine bake this pointer into their kernel nodes
     const size_t need = (size_t)splits * M * N * sizeof(float);
-    const size_t cap = SPLITK_WS_BYTES;
+    const size_t cap = (size_t)8 * 256 * 8192 * sizeof(float);
     B200Q_CHECK_ARG(need <= cap, "split-K scratch too small for M=%d N=%d splits=%d", M, N, splits);
     if (!g_splitk_ws) {
       B200Q_CUDA(cudaMalloc(&g_splitk_ws, cap));
@@ -878,31 +873,6 @@ __global__ void __launch_bounds__(64)
 
 int g_gemm_force_bn = 0;  // test hook: 0 = heuristic
 int g_gemm_splitk = 0;    // 0 = auto, 1 = never, n > 1 = force n splits where legal (tests)
-int g_gemm_mode = 0;      // 0 = auto, 1 = force 1-CTA kernels, 2 = force the 2-CTA kernel
-
-// Mid-sized batches (256 < M <= 1024) and a long reduction (K >= 8192: the down projection): when the
-// 128 x 256 output tiles fill less than one round of the persistent loop (M = 750, N = 4096: 96 tiles
-// on 148 SMs), split K — unevenly if need be (224 k-blocks in 3 parts) — so that tiles x splits is close
-// to a whole number of rounds.  Relative makespan of a split: ceil(tiles*s/SMs)/s, plus ~4 % per split for
-// writing and re-reading the fp32 partials; taken only for a >= 15 % gain.
-static int choose_splits_wide(int M, int N, int K, bool invariant) {
-  if (invariant || g_gemm_splitk == 1 || g_gemm_force_bn != 0 || g_gemm_mode == 2) return 1;
-  if (M <= 256 || M > 1024 || N % 256 != 0 || K / GEMM_BK < 128) return 1;
-  const long long sms = num_sms();
-  const long long t1 = (long long)((M + GEMM_BM - 1) / GEMM_BM) * (N / 256);
-  if (t1 >= sms) return 1;
-  double best = 1.0;
-  int best_s = 1;
-  for (int sN = 2; sN <= 4; ++sN) {
-    if ((size_t)sN * M * N * sizeof(float) > SPLITK_WS_BYTES) break;
-    const double t = (double)((t1 * sN + sms - 1) / sms) / sN + 0.04 * sN;
-    if (t < best - 0.15) {
-      best = t;
-      best_s = sN;
-    }
-  }
-  return best_s;
-}
 
 static bool batch_invariant_env() {
   static const bool v = [] {
@@ -929,7 +899,7 @@ static int choose_splits(int M, int N, int K, bool invariant, int forced_bn) {
   }
   return (splits > 1 && splits <= 8 && kb % splits == 0) ? splits : 1;
 }
-
+int g_gemm_mode = 0;      // 0 = auto, 1 = force 1-CTA kernels, 2 = force the 2-CTA kernel
 
 }  // namespace b200q
 
@@ -1034,8 +1004,6 @@ int b200q_gemm_bf16(const void* A, const void* W, void* C, int M, int N, int K, 
     // VLLM_BATCH_INVARIANT); costs decode-sized GEMMs up to 2x
     const int splits = choose_splits(M, N, K, batch_invariant_env(), bn);
     if (splits > 1) return launch_gemm<128>(A, W, C, M, N, K, st, splits);
-    const int wide = choose_splits_wide(M, N, K, batch_invariant_env());
-    if (wide > 1) return launch_gemm<256>(A, W, C, M, N, K, st, wide);
   }
   if (bn == 0) {
     // Every CTA walks ceil(tiles / SMs) tiles; measured on B200 (profiles/r1_microbench.md) a
@@ -1081,15 +1049,9 @@ int b200q_gemm_bf16_splitk(const void* A, const void* W, int M, int N, int K, vo
                   "gemm: operands must be 16-byte aligned");
   if (M == 0 || g_gemm_mode == 2 || g_gemm_force_bn != 0 || (g_gemm_mode == 0 && prefer_2cta(M, N)))
     return B200Q_OK;
-  int splits = choose_splits(M, N, K, batch_invariant_env(), 0);
-  int rc;
-  if (splits > 1) {
-    rc = launch_gemm<128>(A, W, nullptr, M, N, K, as_stream(stream), splits, partials_out);
-  } else {
-    splits = choose_splits_wide(M, N, K, batch_invariant_env());
-    if (splits <= 1) return B200Q_OK;
-    rc = launch_gemm<256>(A, W, nullptr, M, N, K, as_stream(stream), splits, partials_out);
-  }
+  const int splits = choose_splits(M, N, K, batch_invariant_env(), 0);
+  if (splits <= 1) return B200Q_OK;
+  int rc = launch_gemm<128>(A, W, nullptr, M, N, K, as_stream(stream), splits, partials_out);
   if (rc) return rc;
   *splits_out = splits;
   return B200Q_OK;

@@ -420,38 +420,3 @@ def test_model_forward_is_identical_with_and_without_splitk_fusion(cuda, monkeyp
         eng.close()
         svc.engine.model.close()
     assert outs["1"] == outs["0"]
-
-
-@pytest.mark.parametrize("M,N,K", [(300, 4096, 14336), (750, 4096, 14336), (1024, 3584, 14336), (750, 4096, 8192)])
-def test_gemm_wide_uneven_splitk(cuda, M, N, K):
-    """mid-sized batches with a long reduction (the down projection at 256 < M <= 1024): when the output
-    tiles fill less than one round of the persistent loop the library splits K, unevenly if need be
-    (224 k-blocks in 3 parts).  Against the fp32-accumulate torch reference, against the unsplit kernel
-    (at most the final rounding of a few elements may differ), and through the fused consumer."""
-    from llmq_b200 import lib
-    L = lib.load()
-    a, w = rnd(M, K, seed=31).to(cuda), rnd(N, K, seed=32, scale=0.02).to(cuda)
-    c = torch.full((M, N), float("nan"), dtype=BF, device=cuda)
-    lib.gemm_bf16(a, w, c)
-    part, splits = lib.gemm_bf16_splitk(a, w)
-    expect_split = (M, N, K) != (1024, 3584, 14336)   # 8 x 14 = 112 tiles: no split pays there
-    assert (splits > 1) == expect_split, splits
-    ref = (a.float() @ w.float().t()).to(BF)
-    atol = 2e-5 * math.sqrt(K)
-    bf16_close(c, ref.cpu(), ulps=1.0, atol=atol, max_mismatch_frac=0.02, what=f"wide split-K gemm {M}x{N}x{K}")
-    lib.check(L.b200q_gemm_set_splitk(1))
-    try:
-        c1 = torch.empty_like(c)
-        lib.gemm_bf16(a, w, c1)
-    finally:
-        lib.check(L.b200q_gemm_set_splitk(0))
-    bf16_close(c, c1.cpu(), ulps=1.0, atol=atol, max_mismatch_frac=0.02, what="split vs unsplit")
-    if splits > 1:
-        res0, wn = rnd(M, N, seed=33, scale=2.0).to(cuda), rnd(N, seed=34).to(cuda)
-        x, r = torch.empty(M, N, dtype=BF, device=cuda), res0.clone()
-        lib.add_rmsnorm_splitk(x, r, wn, part, splits, 1e-5)
-        r_ref = res0.clone()
-        c2 = c.clone()
-        lib.add_rmsnorm(c2, r_ref, wn, 1e-5)
-        torch.cuda.synchronize()
-        assert torch.equal(r, r_ref) and torch.equal(x, c2), "fused consumer must equal reduce + add_rmsnorm"

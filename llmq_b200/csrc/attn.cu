@@ -108,7 +108,7 @@ __device__ __forceinline__ void pv_page(uint32_t v_s, const float (&p)[BS / 8][4
 // Which decode formulation a head size uses.  Measured on B200 (bench, Llama-3-8B, D = 128): the
 // row-major PV form streams 6.2 TB/s, the transposed form 5.8 TB/s (two extra shuffles sit on the
 // per-page dependency chain); at D = 256 the row-major form needs 128 accumulator registers, spills
-// and runs one CTA per SM, so the transposed form (64 registers, no spills, 2 CTAs/SM) is used there.
+// so the transposed form (64 accumulator registers, no spills) is used there: 6.3 TB/s on Gemma-2-9B.
 template <int D>
 constexpr bool kTransposedPV = D >= 256;
 

@@ -65,3 +65,23 @@ def test_two_worker_processes_share_one_queue(tmp_path):
                 p.wait(5)
             except Exception:
                 p.kill()
+
+
+def test_queue_bench_tool_pipeline_mode_with_the_reference_dummy_worker(tmp_path):
+    """tools/queue_bench.py (the process-level harness of BASELINE configs #3-#5) in its two-stage pipeline
+    mode, with the reference's own DummyWorker processes standing in for the GPU workers: broker process,
+    `llmq worker pipeline CFG STAGE` processes, stage-1 results routed to stage 2 by the reference's
+    publish_pipeline_result, final results counted from `pipeline.<name>.results`."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "queue_bench.py"), "--worker-kind", "dummy",
+                        "--pipeline", "1+1", "--jobs", "12", "--prefetch", "20", "--out-dir", str(tmp_path), "--timeout", "120"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["config"] == "#4 two-stage pipeline" and d["jobs"] == 12 and d["workers"] == "1+1"
+    q = d["queues_at_end"]
+    assert q["pipeline.qbench.stage1"]["delivered"] == 12 and q["pipeline.qbench.stage2"]["delivered"] == 12
